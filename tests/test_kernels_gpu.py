@@ -368,3 +368,51 @@ def test_attn_fwd_cross_attention_shape(ops):
     ro, rl = _sdpa_ref(q.float(), kv[:, 0].float(), kv[:, 1].float(), [(0, n, M)], D ** -0.5)
     close(o, ro)
     close(lse, rl, rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("n,H,segs", [
+    (256, 2, [(0, 256, 256)]),
+    (1024, 4, [(0, 512, 512), (512, 1024, 1024)]),
+    (1000, 3, [(0, 390, 390), (390, 1000, 1000)]),
+    (3120, 2, [(0, 1560, 1560), (1560, 3120, 3120)]),
+])
+def test_attn_bwd(ops, n, H, segs):
+    D = 128
+    scale = D ** -0.5
+    qkv = rnd(n, 3, H, D, seed=1)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    o = torch.zeros(n, H, D, dtype=BF16, device="cuda")
+    lse = torch.zeros(H, n, dtype=F32, device="cuda")
+    ops.attn_fwd(q, k, v, o, lse, segs, scale)
+    do = rnd(n, H, D, seed=2)
+    dqkv = torch.full((n, 3, H, D), float("nan"), dtype=BF16, device="cuda")
+    delta = torch.empty(H, n, dtype=F32, device="cuda")
+    ops.attn_bwd(dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], do, o, lse, delta, q, k, v, segs, scale)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ro, _ = _sdpa_ref(qf, kf, vf, segs, scale)
+    ro.backward(do.float())
+    close(delta, (do.float() * o.float()).sum(-1).t(), rtol=2e-2)
+    close(dqkv[:, 0], qf.grad)
+    close(dqkv[:, 1], kf.grad)
+    close(dqkv[:, 2], vf.grad)
+
+
+def test_attn_bwd_cross_attention_shape(ops):
+    n, M, H, D = 700, 128, 4, 128
+    scale = D ** -0.5
+    q, kv = rnd(n, H, D, seed=1), rnd(M, 2, H, D, seed=2)
+    o = torch.zeros(n, H, D, dtype=BF16, device="cuda")
+    lse = torch.zeros(H, n, dtype=F32, device="cuda")
+    segs = [(0, n, M)]
+    ops.attn_fwd(q, kv[:, 0], kv[:, 1], o, lse, segs, scale)
+    do = rnd(n, H, D, seed=3)
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    delta = torch.empty(H, n, dtype=F32, device="cuda")
+    ops.attn_bwd(dq, dkv[:, 0], dkv[:, 1], do, o, lse, delta, q, kv[:, 0], kv[:, 1], segs, scale)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, kv[:, 0], kv[:, 1]))
+    ro, _ = _sdpa_ref(qf, kf, vf, segs, scale)
+    ro.backward(do.float())
+    close(dq, qf.grad)
+    close(dkv[:, 0], kf.grad)
+    close(dkv[:, 1], vf.grad)
