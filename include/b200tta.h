@@ -193,6 +193,16 @@ int b200tta_patchify(void* P, const void* latent, int32_t T, int32_t H, int32_t 
 /* tokens [T*H/2*W/2, 64] f32 (final-layer order) -> latent [16,T,H,W] f32 */
 int b200tta_unpatchify(float* latent, const float* tokens, int32_t T, int32_t H, int32_t W, b200tta_stream_t stream);
 
+/* d(pred): latent-layout f32 gradient [16,T,H,W] -> token-layout bf16 [(T - t_begin)*H/2*W/2, 64] (frames >= t_begin) */
+int b200tta_latent_to_tokens(void* tokens, const float* latent, int32_t T, int32_t H, int32_t W, int32_t t_begin,
+                             b200tta_stream_t stream);
+
+/* standalone SwiGLU (used when w1/w3 carry LoRA adapters and cannot be co-tiled): h = silu(h1) * h3 over n bf16
+ * elements, and its backward (dh1, dh3) from dh. */
+int b200tta_swiglu_fwd(void* Hout, const void* H1, const void* H3, int64_t n, b200tta_stream_t stream);
+int b200tta_swiglu_bwd(void* dH1, void* dH3, const void* dH, const void* H1, const void* H3, int64_t n,
+                       b200tta_stream_t stream);
+
 /* loss += mean((pred - V)^2) over n elements; dpred = bf16(2 (pred - V) / n * loss_scale). loss must be zeroed. */
 int b200tta_mse_fwd_bwd(float* loss, void* dpred, const float* pred, const float* V, int64_t n, float loss_scale,
                         b200tta_stream_t stream);

@@ -58,6 +58,9 @@ SIGNATURES = {
     "b200tta_noise_patchify": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, f32, vp],
     "b200tta_patchify": [vp, vp, i32, i32, i32, vp],
     "b200tta_unpatchify": [vp, vp, i32, i32, i32, vp],
+    "b200tta_latent_to_tokens": [vp, vp, i32, i32, i32, i32, vp],
+    "b200tta_swiglu_fwd": [vp, vp, vp, i64, vp],
+    "b200tta_swiglu_bwd": [vp, vp, vp, vp, vp, i64, vp],
     "b200tta_mse_fwd_bwd": [vp, vp, vp, vp, i64, f32, vp],
     "b200tta_timestep_sinusoid": [vp, vp, i32, i32, vp],
     "b200tta_skinny_linear": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],

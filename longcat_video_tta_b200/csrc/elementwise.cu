@@ -540,6 +540,51 @@ __global__ void __launch_bounds__(256) skinny_linear_bwd_kernel(float* __restric
     (void)accumulate;
 }
 
+
+// ------------------------------------------------------------------------------------ standalone SwiGLU
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(__nv_bfloat16* __restrict__ Hout, const __nv_bfloat16* __restrict__ H1,
+                                                         const __nv_bfloat16* __restrict__ H3, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(H1) + i), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(H3) + i), b);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = a[k] / (1.0f + __expf(-a[k])) * b[k];
+        reinterpret_cast<uint4*>(Hout)[i] = pack8(a);
+    }
+}
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(__nv_bfloat16* __restrict__ dH1, __nv_bfloat16* __restrict__ dH3,
+                                                         const __nv_bfloat16* __restrict__ dH, const __nv_bfloat16* __restrict__ H1,
+                                                         const __nv_bfloat16* __restrict__ H3, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float a[8], b[8], g[8], o1[8], o3[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(H1) + i), a);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(H3) + i), b);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(dH) + i), g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float sig = 1.0f / (1.0f + __expf(-a[k]));
+            o1[k] = g[k] * b[k] * sig * (1.0f + a[k] * (1.0f - sig));
+            o3[k] = g[k] * a[k] * sig;
+        }
+        reinterpret_cast<uint4*>(dH1)[i] = pack8(o1);
+        reinterpret_cast<uint4*>(dH3)[i] = pack8(o3);
+    }
+}
+// latent f32 [16,T,H,W] -> tokens bf16 [n, 64] in final-layer column order (inverse of unpatchify; used for d(pred))
+__global__ void __launch_bounds__(256) latent_to_tokens_kernel(__nv_bfloat16* __restrict__ tok, const float* __restrict__ latent,
+                                                               int T, int H, int W, int t0) {
+    const int H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)(T - t0) * H2 * W2 * 64;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i & 63);
+        const long long n = i >> 6;
+        const int c = col & 15, pw = (col >> 4) & 1, ph = col >> 5;
+        const int w2 = (int)(n % W2), h2 = (int)((n / W2) % H2), t = (int)(n / ((long long)W2 * H2)) + t0;
+        tok[i] = __float2bfloat16(latent[(((long long)c * T + t) * H + 2 * h2 + ph) * W + 2 * w2 + pw]);
+    }
+}
+
 inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
     long long g = (work_items + per_block - 1) / per_block;
     if (g < 1) g = 1;
@@ -757,6 +802,36 @@ extern "C" int b200tta_skinny_linear_bwd(float* dX, const float* dY, const float
     }
     skinny_linear_bwd_kernel<<<g, 256, smem, st>>>(dX, dY, X, W, w_bf16, R, in_features, out_features, act, accumulate,
                                                    out_chunk);
+    B200_CUDA(cudaGetLastError());
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_swiglu_fwd(void* Hout, const void* H1, const void* H3, int64_t n, b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(Hout && H1 && H3 && n > 0 && n % 8 == 0 && aligned16(Hout) && aligned16(H1) && aligned16(H3), "swiglu_fwd: bad arguments");
+    swiglu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)Hout, (const __nv_bfloat16*)H1,
+                                                                              (const __nv_bfloat16*)H3, n / 8);
+    B200_CUDA(cudaGetLastError());
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_swiglu_bwd(void* dH1, void* dH3, const void* dH, const void* H1, const void* H3, int64_t n,
+                                  b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(dH1 && dH3 && dH && H1 && H3 && n > 0 && n % 8 == 0 && aligned16(dH1) && aligned16(dH3) && aligned16(dH) &&
+                     aligned16(H1) && aligned16(H3), "swiglu_bwd: bad arguments");
+    swiglu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)dH1, (__nv_bfloat16*)dH3, (const __nv_bfloat16*)dH, (const __nv_bfloat16*)H1, (const __nv_bfloat16*)H3, n / 8);
+    B200_CUDA(cudaGetLastError());
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_latent_to_tokens(void* tokens, const float* latent, int32_t T, int32_t H, int32_t W, int32_t t_begin,
+                                        b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(tokens && latent && T > 0 && t_begin >= 0 && t_begin < T && H % 2 == 0 && W % 2 == 0, "latent_to_tokens: bad arguments");
+    const long long total = (long long)(T - t_begin) * (H / 2) * (W / 2) * 64;
+    latent_to_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)tokens, latent, T, H, W, t_begin);
     B200_CUDA(cudaGetLastError());
     return B200TTA_OK;
 }

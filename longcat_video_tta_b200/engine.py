@@ -1,0 +1,677 @@
+"""TTAEngine: runs the DiT forward, the adapter-only backward and the optimizer step with the sm_100a kernels.
+
+Execution plan (per step, batch 1 as in every reference run -- common.py:458-463):
+  noise+patchify -> patch-embed GEMM -> [48 x block forward, block inputs kept] -> final layer -> MSE (+ d pred)
+  -> final-layer backward -> [48 x (re-run block forward into one reusable workspace, block backward)]
+  -> adapter gradients in ONE flat fp32 buffer (the thing a data-parallel run all-reduces)
+  -> multi-tensor clip + AdamW.
+Frozen weights never get a gradient: every base GEMM backward is dX only (MN-major B operand, no transposed
+copies).  Per-block recompute mirrors the reference's ``torch.utils.checkpoint`` policy
+(lora_experiment/scripts/run_lora_tta.py:806-811) but lives in a single pre-allocated workspace.
+
+What is saved where (HBM layout, N tokens, C hidden, F ffn):
+  xs[L+1][N,C] bf16      block inputs (checkpoints) and the final hidden state
+  ws.*                   one block's intermediates: xm1, qkv, qk(normed+roped), o, lse, x1, xn, qc, qcn, kvc, kcn, oc,
+                         lsec, x2, xm2, h1, h3, h and the gradient temporaries; re-used by every block
+  grad_flat f32          all adapter gradients back to back (LoRA "down" gradients transposed, see b200tta.h)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+# ---------------------------------------------------------------------------------------------------- geometry
+@dataclass(frozen=True)
+class Geometry:
+    T: int        # latent frames (cond + target)
+    Hl: int       # latent height
+    Wl: int       # latent width
+    n_cond: int   # clean-context latent frames
+    M: int        # packed text tokens
+
+    @property
+    def gh(self): return self.Hl // 2
+    @property
+    def gw(self): return self.Wl // 2
+    @property
+    def tpf(self): return self.gh * self.gw
+    @property
+    def N(self): return self.T * self.tpf
+    @property
+    def Nc(self): return self.n_cond * self.tpf
+    @property
+    def Nn(self): return self.N - self.Nc
+
+    def self_segments(self):
+        if self.Nc == 0:
+            return [(0, self.N, self.N)]
+        return [(0, self.Nc, self.Nc), (self.Nc, self.N, self.N)]
+
+
+# ---------------------------------------------------------------------------------------------------- adapter sites
+class LinearSite:
+    """One linear of the block as the kernels see it: frozen W / bias plus an optional rank-r adapter.
+
+    Recognised adapter forms (duck-typed):
+      * a wrapper with ``.original`` / ``.lora_down`` / ``.lora_up`` / ``.scaling``  (reference ``LoRALinear``,
+        run_lora_tta.py:224-260, or ours);
+      * a plain ``nn.Linear`` carrying ``._b200_lora`` (builtin-style ``LoRAModule``: ``lora_down`` [n_sep*r, in],
+        ``lora_up`` Linear or ``.blocks[i]``, ``multiplier * alpha_scale``; run_lora_tta.py:132-135,175-181).
+    """
+
+    def __init__(self, module: nn.Module, name: str):
+        self.name = name
+        self.params: List[nn.Parameter] = []
+        self.blocks_up = None
+        lin = module
+        self.r = 0
+        self.scale = 1.0
+        down = up = None
+        if hasattr(module, "original") and hasattr(module, "lora_down") and hasattr(module, "lora_up"):
+            lin = module.original
+            down, up = module.lora_down, module.lora_up
+            self.scale = float(getattr(module, "scaling", 1.0))
+            if getattr(module, "dropout", None) is not None and isinstance(module.dropout, nn.Dropout) and module.dropout.p > 0:
+                raise NotImplementedError("LoRA dropout > 0 is not supported by the fused kernels (reference default is 0.0)")
+        elif getattr(module, "_b200_lora", None) is not None:
+            lora = module._b200_lora
+            if getattr(lora, "use_lora", True):
+                down, up = lora.lora_down, lora.lora_up
+                self.scale = float(lora.multiplier) * float(lora.alpha_scale)
+        if not isinstance(lin, nn.Linear):
+            raise TypeError(f"{name}: expected nn.Linear (or a LoRA wrapper around one), got {type(lin).__name__}")
+        self.W, self.bias = lin.weight, lin.bias
+        self.out_features, self.in_features = lin.weight.shape
+        if down is not None:
+            self.A_param = down.weight                       # [r_total, in]
+            self.r_total = down.weight.shape[0]
+            if hasattr(up, "blocks"):                        # n_separate > 1: block-diagonal up projection
+                self.blocks_up = [b.weight for b in up.blocks]
+                self.params = [self.A_param, *self.blocks_up]
+            else:
+                self.B_param = up.weight                     # [out, r]
+                self.params = [self.A_param, self.B_param]
+            self.r = (self.r_total + 7) // 8 * 8
+            if self.r > 64:
+                raise NotImplementedError(f"{name}: effective LoRA rank {self.r_total} > 64 is not supported")
+            self.staged = self.blocks_up is not None or self.r != self.r_total
+        # filled by the engine
+        self.A = self.B = None          # bf16 tensors the kernels read ([r, in], [out, r])
+        self.dA_acc = self.dB_acc = None  # f32 views into grad_flat ([in, r], [out, r])
+
+    @property
+    def has_lora(self):
+        return self.r > 0
+
+    def refresh(self):
+        """(Re)build the kernel-facing A/B when they are staged copies (rank padding / block-diagonal up)."""
+        if not self.has_lora:
+            return
+        if not self.staged:
+            self.A, self.B = self.A_param.detach(), self.B_param.detach()
+            return
+        dev = self.A_param.device
+        if self.A is None:
+            self.A = torch.zeros(self.r, self.in_features, dtype=BF16, device=dev)
+            self.B = torch.zeros(self.out_features, self.r, dtype=BF16, device=dev)
+        self.A[: self.r_total].copy_(self.A_param.detach())
+        if self.blocks_up is not None:
+            n = len(self.blocks_up)
+            rr, oo = self.r_total // n, self.out_features // n
+            for i, w in enumerate(self.blocks_up):
+                self.B[i * oo:(i + 1) * oo, i * rr:(i + 1) * rr].copy_(w.detach())
+        else:
+            self.B[:, : self.r_total].copy_(self.B_param.detach())
+
+    def param_grads(self) -> List[torch.Tensor]:
+        """fp32 gradients in the parameters' own layout (views / small copies of the flat accumulators)."""
+        gA = self.dA_acc.t()[: self.r_total]
+        if self.blocks_up is not None:
+            n = len(self.blocks_up)
+            rr, oo = self.r_total // n, self.out_features // n
+            return [gA] + [self.dB_acc[i * oo:(i + 1) * oo, i * rr:(i + 1) * rr] for i in range(n)]
+        return [gA, self.dB_acc[:, : self.r_total]]
+
+
+SITE_NAMES = ("qkv", "proj", "q_linear", "kv_linear", "cproj", "w1", "w2", "w3")
+
+
+def _block_sites(blk, i: int) -> Dict[str, LinearSite]:
+    return {
+        "qkv": LinearSite(blk.attn.qkv, f"blocks.{i}.attn.qkv"),
+        "proj": LinearSite(blk.attn.proj, f"blocks.{i}.attn.proj"),
+        "q_linear": LinearSite(blk.cross_attn.q_linear, f"blocks.{i}.cross_attn.q_linear"),
+        "kv_linear": LinearSite(blk.cross_attn.kv_linear, f"blocks.{i}.cross_attn.kv_linear"),
+        "cproj": LinearSite(blk.cross_attn.proj, f"blocks.{i}.cross_attn.proj"),
+        "w1": LinearSite(blk.ffn.w1, f"blocks.{i}.ffn.w1"),
+        "w2": LinearSite(blk.ffn.w2, f"blocks.{i}.ffn.w2"),
+        "w3": LinearSite(blk.ffn.w3, f"blocks.{i}.ffn.w3"),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------- extras (delta / norm / FiLM)
+class Extras:
+    """Optional non-LoRA trainables of one step (delta / norm-tune / FiLM methods).  All default to "absent".
+
+    t_offset[b]      f32 [C_t]   added to the timestep embedding seen by block b (delta-A: same vector for every
+                                 block and the final layer; delta-B timestep: per group)         run_delta_a.py:168
+    t_offset_final   f32 [C_t]   offset seen by the final layer (delta-A only)
+    film[b]          f32 [6C]    added to block b's adaLN output (FiLM, already expanded)          run_film_tta.py:129-144
+    hidden[b]        f32 [C]     added to block b's output (delta-B hidden), hidden_final likewise  run_delta_b.py:318-324
+    out_bias         f32 [16]    added to the prediction per channel (delta-C)                     run_delta_c.py:164-166
+    norm_grads       bool        accumulate gradients of pre_crs_attn_norm / q,k RMSNorm weights   run_norm_tune_tta.py:74-98
+    need_dt / need_dmod          which modulation-side gradients the backward must produce
+    """
+
+    def __init__(self, depth: int):
+        self.t_offset: List[Optional[torch.Tensor]] = [None] * depth
+        self.t_offset_final: Optional[torch.Tensor] = None
+        self.film: List[Optional[torch.Tensor]] = [None] * depth
+        self.hidden: List[Optional[torch.Tensor]] = [None] * depth
+        self.hidden_final: Optional[torch.Tensor] = None
+        self.out_bias: Optional[torch.Tensor] = None
+        self.norm_grads = False
+        self.need_dt = False
+        self.need_dmod = False
+        # outputs of the backward
+        self.d_t: List[Optional[torch.Tensor]] = [None] * depth      # f32 [T, C_t] per block
+        self.d_t_final: Optional[torch.Tensor] = None
+        self.d_mod: List[Optional[torch.Tensor]] = [None] * depth    # f32 [T, 6C] per block
+        self.d_hidden: List[Optional[torch.Tensor]] = [None] * depth  # f32 [C]
+        self.d_hidden_final: Optional[torch.Tensor] = None
+        self.d_out_bias: Optional[torch.Tensor] = None
+        self.d_norm: Dict[str, torch.Tensor] = {}
+
+
+class _WS:
+    pass
+
+
+# ---------------------------------------------------------------------------------------------------- engine
+class TTAEngine:
+    def __init__(self, dit):
+        self.dit = dit
+        cfg = dit.config
+        self.C, self.F, self.H, self.D = cfg.hidden_size, cfg.ffn_dim, cfg.num_heads, cfg.head_dim
+        self.L, self.Ct = cfg.depth, cfg.adaln_tembed_dim
+        self.softmax_scale = self.D ** -0.5
+        self.geo: Optional[Geometry] = None
+        self.ws = None
+        self.sites: List[Dict[str, LinearSite]] = []
+        self._site_sig = None
+        self.grad_flat: Optional[torch.Tensor] = None
+        self._text_cache = None
+        self.device = dit.x_embedder.proj.weight.device
+        if dit.x_embedder.proj.weight.dtype != BF16:
+            raise TypeError("B200DiT parameters must be bf16 (the kernels read them in place)")
+
+    # ------------------------------------------------------------------ adapters
+    def _signature(self):
+        sig = []
+        for blk in self.dit.blocks:
+            for m in (blk.attn.qkv, blk.attn.proj, blk.cross_attn.q_linear, blk.cross_attn.kv_linear, blk.cross_attn.proj,
+                      blk.ffn.w1, blk.ffn.w2, blk.ffn.w3):
+                sig.append((id(m), id(getattr(m, "_b200_lora", None))))
+        return tuple(sig)
+
+    def resolve_sites(self, force: bool = False):
+        sig = self._signature()
+        if not force and sig == self._site_sig:
+            return
+        self._site_sig = sig
+        self.sites = [_block_sites(blk, i) for i, blk in enumerate(self.dit.blocks)]
+        total = 0
+        for bs in self.sites:
+            for s in bs.values():
+                if s.has_lora:
+                    total += (s.in_features + s.out_features) * s.r
+        self.grad_flat = torch.zeros(max(total, 1), dtype=F32, device=self.device)
+        off = 0
+        for bs in self.sites:
+            for nm in SITE_NAMES:
+                s = bs[nm]
+                if s.has_lora:
+                    s.dA_acc = self.grad_flat[off: off + s.in_features * s.r].view(s.in_features, s.r)
+                    off += s.in_features * s.r
+                    s.dB_acc = self.grad_flat[off: off + s.out_features * s.r].view(s.out_features, s.r)
+                    off += s.out_features * s.r
+        self.max_r = max([s.r for bs in self.sites for s in bs.values()] + [0])
+        if self.ws is not None:
+            self._alloc_lora_ws()
+
+    def lora_sites(self) -> List[LinearSite]:
+        return [bs[nm] for bs in self.sites for nm in SITE_NAMES if bs[nm].has_lora]
+
+    def adapter_parameters(self) -> List[nn.Parameter]:
+        self.resolve_sites()
+        return [p for s in self.lora_sites() for p in s.params]
+
+    # ------------------------------------------------------------------ workspace
+    def plan(self, geo: Geometry):
+        """Allocate (once per geometry; train and early-stopping geometries are both kept) the step workspace."""
+        if self.geo == geo and self.ws is not None:
+            return
+        self._ws_holds = None
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        if geo in cache:
+            self.geo, self.ws = geo, cache[geo]
+            self._alloc_lora_ws()
+            return
+        if len(cache) >= 2:
+            cache.clear()
+        self.geo = geo
+        dev, C, F, H = self.device, self.C, self.F, self.H
+        N, Nn, M, T = geo.N, geo.Nn, geo.M, geo.T
+        e = lambda *s, dt=BF16: torch.empty(*s, dtype=dt, device=dev)
+        ws = _WS()
+        ws.xs = e(self.L + 1, N, C)
+        ws.P = e(N, 64)
+        ws.V = e(max(Nn, 1), 64, dt=F32)
+        ws.timestep = e(T, dt=F32)
+        ws.tfeat, ws.th, ws.t = e(T, self.dit.config.frequency_embedding_size, dt=F32), e(T, self.Ct, dt=F32), e(T, self.Ct, dt=F32)
+        ws.t_blk = e(T, self.Ct, dt=F32)
+        ws.y1, ws.y = e(M, C), e(M, C)
+        ws.mod, ws.modf = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32)
+        ws.xm1, ws.xm2 = e(N, C), e(N, C)
+        ws.qkv, ws.qk, ws.o = e(N, 3 * C), e(N, 2 * C), e(N, C)
+        ws.lse, ws.delta = e(H, N, dt=F32), e(H, N, dt=F32)
+        ws.x1, ws.x2 = e(N, C), e(N, C)
+        ws.xn, ws.qc, ws.qcn, ws.oc = e(Nn, C), e(Nn, C), e(Nn, C), e(Nn, C)
+        ws.kvc, ws.kcn = e(M, 2 * C), e(M, C)
+        ws.lsec, ws.deltac = e(H, Nn, dt=F32), e(H, Nn, dt=F32)
+        ws.h, ws.h1, ws.h3 = e(N, F), e(N, F), e(N, F)
+        ws.xf, ws.pred = e(N, C), e(N, 64, dt=F32)
+        # backward temporaries
+        ws.dx = e(N, C)
+        ws.g1, ws.g2 = e(N, C), e(N, C)
+        ws.dh1, ws.dh3 = e(N, F), e(N, F)
+        ws.dqkv, ws.dqk = e(N, 3 * C), e(N, 2 * C)
+        ws.dqc, ws.dkvc = e(Nn, C), e(M, 2 * C)
+        ws.dpred = e(max(Nn, 1), 64)
+        ws.loss = torch.zeros(1, dtype=F32, device=dev)
+        ws.dmod, ws.dmodf, ws.dt = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32), e(T, self.Ct, dt=F32)
+        ws.branch_a = ws.branch_m = None  # branch outputs, allocated on demand (FiLM / delta gate gradients)
+        self.ws = ws
+        cache[geo] = ws
+        self._alloc_lora_ws()
+
+    def _alloc_lora_ws(self):
+        ws, geo = self.ws, self.geo
+        r = max(getattr(self, "max_r", 0), 8)
+        if getattr(ws, "xa_r", 0) >= r:
+            return
+        ws.xa_r = r
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=self.device)
+        rows = max(geo.N, geo.M)
+        # XA of every LoRA'd linear of one block is kept between the block's forward and backward
+        ws.xa = {nm: e(rows, r) for nm in SITE_NAMES}
+        ws.u = e(rows, r)
+
+    # ------------------------------------------------------------------ small pieces
+    def _xa(self, s, nm, rows):
+        return self.ws.xa[nm].view(-1)[: rows * s.r].view(rows, s.r)
+
+    def _linear_bwd(self, s: LinearSite, dy, x, e, nm):
+        if s.has_lora:
+            rows = dy.shape[0]
+            u = self.ws.u.view(-1)[: rows * s.r].view(rows, s.r)
+            ops.lora_linear_bwd(dy, s.W, e, x=x, A=s.A, B=s.B, XA=self._xa(s, nm, rows), U=u, dA_acc=s.dA_acc,
+                                dB_acc=s.dB_acc, scale=s.scale)
+        elif e is not None:
+            ops.lora_linear_bwd(dy, s.W, e)
+
+    def _linear_fwd_xa(self, s, x, e, nm):
+        if s.has_lora:
+            ops.lora_linear_fwd(x, s.W, e, A=s.A, B=s.B, XA=self._xa(s, nm, x.shape[0]), scale=s.scale)
+        else:
+            ops.lora_linear_fwd(x, s.W, e)
+
+    # ------------------------------------------------------------------ text / time embeddings
+    def pack_text(self, prompt_embeds: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
+        """[B=1,1,Ltxt,Cc] (+ mask [1,Ltxt]) -> valid rows [M, Cc] bf16 (run_delta_a.py:170-192: y_embedder is
+        row-wise, so packing the valid tokens before or after it is the same arithmetic)."""
+        key = (prompt_embeds.data_ptr(), prompt_embeds._version, None if mask is None else (mask.data_ptr(), mask._version))
+        if self._text_cache is not None and self._text_cache[0] == key:
+            return self._text_cache[1]
+        pe = prompt_embeds.reshape(-1, prompt_embeds.shape[-1])
+        if prompt_embeds.shape[0] != 1:
+            raise NotImplementedError("batch size 1 only (as in every reference run)")
+        if mask is not None:
+            idx = mask.reshape(-1).nonzero(as_tuple=False).flatten()
+            pe = pe.index_select(0, idx.to(pe.device))
+        pe = pe.to(device=self.device, dtype=BF16).contiguous()
+        self._text_cache = (key, pe)
+        return pe
+
+    def _embed_text(self, text_valid):
+        ws, ye = self.ws, self.dit.y_embedder.y_proj
+        M = text_valid.shape[0]
+        ops.gemm(M, self.C, [(text_valid, ye[0].weight, text_valid.shape[1], False, None)],
+                 ops.epi(ops.EPI_GELU, ws.y1, bias=ye[0].bias))
+        ops.gemm(M, self.C, [(ws.y1, ye[2].weight, self.C, False, None)], ops.epi(ops.EPI_STORE, ws.y, bias=ye[2].bias))
+
+    def _embed_time(self):
+        ws, te = self.ws, self.dit.t_embedder
+        ops.timestep_sinusoid(ws.tfeat, ws.timestep)
+        ops.skinny_linear(ws.th, ws.tfeat, te.mlp[0].weight, te.mlp[0].bias)
+        ops.skinny_linear(ws.t, ws.th, te.mlp[2].weight, te.mlp[2].bias, act=1)
+        if te._forward_hooks:  # generation-time hooks (e.g. DeltaAWrapper.apply_to_dit); forward only
+            t = ws.t
+            for hook in te._forward_hooks.values():
+                out = hook(te, (ws.timestep,), t)
+                if out is not None:
+                    t = out
+            ws.t.copy_(t)
+
+    def _t_for_block(self, b, ex: Optional[Extras]):
+        if ex is not None and ex.t_offset[b] is not None:
+            torch.add(self.ws.t, ex.t_offset[b].to(F32)[None, :], out=self.ws.t_blk)
+            return self.ws.t_blk
+        return self.ws.t
+
+    # ------------------------------------------------------------------ block forward
+    def _block_fwd(self, b: int, x_in, x_out, ex: Optional[Extras]):
+        ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
+        blk, st = self.dit.blocks[b], self.sites[b]
+        N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
+        ada = blk.adaLN_modulation[1]
+        film = None
+        if ex is not None and ex.film[b] is not None:
+            film = ex.film[b].to(F32)[None, :].expand(geo.T, -1).contiguous()
+        elif blk.adaLN_modulation._forward_hooks:
+            raise NotImplementedError("forward hooks on adaLN_modulation: use longcat_video_tta_b200.film.FiLMAdapterWrapper")
+        ops.skinny_linear(ws.mod, self._t_for_block(b, ex), ada.weight, ada.bias, act=1, addend=film)
+        mod = ws.mod
+        shift_msa, scale_msa, gate_msa = mod[:, 0:C], mod[:, C:2 * C], mod[:, 2 * C:3 * C]
+        shift_mlp, scale_mlp, gate_mlp = mod[:, 3 * C:4 * C], mod[:, 4 * C:5 * C], mod[:, 5 * C:6 * C]
+        keep_branch = ex is not None and ex.need_dmod
+
+        # ---- self attention
+        ops.ln_mod_fwd(ws.xm1, x_in, scale_msa, shift_msa, tokens_per_frame=tpf)
+        s = st["qkv"]
+        self._linear_fwd_xa(s, ws.xm1, ops.epi(ops.EPI_STORE, ws.qkv, bias=s.bias), "qkv")
+        ops.qk_rmsnorm_rope_fwd(ws.qk, ws.qkv, blk.attn.q_norm.weight, blk.attn.k_norm.weight, H, H,
+                                grid_hw=(geo.gh, geo.gw), rope_base=self.dit.config.rope_base)
+        q = ws.qk.view(N, 2 * H, D)[:, :H]
+        k = ws.qk.view(N, 2 * H, D)[:, H:]
+        v = ws.qkv.view(N, 3 * H, D)[:, 2 * H:]
+        ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
+        s = st["proj"]
+        self._linear_fwd_xa(s, ws.o, ops.epi(ops.EPI_GATE_RESID, ws.x1, bias=s.bias, resid=x_in, gate=gate_msa,
+                                             tokens_per_frame=tpf, d2=ws.branch_a if keep_branch else None), "proj")
+        # ---- cross attention (noise tokens only; context rows pass through)
+        if Nn > 0:
+            nrm = blk.pre_crs_attn_norm
+            ops.ln_mod_fwd(ws.xn, ws.x1[Nc:], nrm.weight, nrm.bias, tokens_per_frame=tpf, affine=True)
+            s = st["q_linear"]
+            self._linear_fwd_xa(s, ws.xn, ops.epi(ops.EPI_STORE, ws.qc, bias=s.bias), "q_linear")
+            s = st["kv_linear"]
+            self._linear_fwd_xa(s, ws.y, ops.epi(ops.EPI_STORE, ws.kvc, bias=s.bias), "kv_linear")
+            ops.qk_rmsnorm_rope_fwd(ws.qcn, ws.qc, blk.cross_attn.q_norm.weight, None, H, 0, rope=False)
+            ops.qk_rmsnorm_rope_fwd(ws.kcn, ws.kvc[:, :C], blk.cross_attn.k_norm.weight, None, H, 0, rope=False)
+            vc = ws.kvc.view(M, 2 * H, D)[:, H:]
+            ops.attn_fwd(ws.qcn.view(Nn, H, D), ws.kcn.view(M, H, D), vc, ws.oc.view(Nn, H, D), ws.lsec,
+                         [(0, Nn, M)], self.softmax_scale)
+            if Nc > 0:
+                ws.x2[:Nc].copy_(ws.x1[:Nc])
+            s = st["cproj"]
+            self._linear_fwd_xa(s, ws.oc, ops.epi(ops.EPI_GATE_RESID, ws.x2[Nc:], bias=s.bias, resid=ws.x1[Nc:]), "cproj")
+        else:
+            ws.x2.copy_(ws.x1)
+        # ---- FFN
+        ops.ln_mod_fwd(ws.xm2, ws.x2, scale_mlp, shift_mlp, tokens_per_frame=tpf)
+        s1, s3, s2 = st["w1"], st["w3"], st["w2"]
+        if s1.has_lora or s3.has_lora:
+            self._linear_fwd_xa(s1, ws.xm2, ops.epi(ops.EPI_STORE, ws.h1), "w1")
+            self._linear_fwd_xa(s3, ws.xm2, ops.epi(ops.EPI_STORE, ws.h3), "w3")
+            ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
+        else:
+            ops.lora_linear_fwd(ws.xm2, s1.W, ops.epi(ops.EPI_SWIGLU, ws.h, d2=ws.h1, d3=ws.h3), W_hi=s3.W)
+        self._linear_fwd_xa(s2, ws.h, ops.epi(ops.EPI_GATE_RESID, x_out, resid=ws.x2, gate=gate_mlp, tokens_per_frame=tpf,
+                                              d2=ws.branch_m if keep_branch else None), "w2")
+        if ex is not None and ex.hidden[b] is not None:
+            x_out.add_(ex.hidden[b].to(BF16)[None, :])
+        self._ws_holds = b
+
+    # ------------------------------------------------------------------ block backward (dx in ws.dx, in place)
+    def _block_bwd(self, b: int, x_in, ex: Optional[Extras]):
+        ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
+        blk, st = self.dit.blocks[b], self.sites[b]
+        N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
+        mod = ws.mod
+        scale_msa, gate_msa = mod[:, C:2 * C], mod[:, 2 * C:3 * C]
+        scale_mlp, gate_mlp = mod[:, 4 * C:5 * C], mod[:, 5 * C:6 * C]
+        dx = ws.dx
+        want_mod = ex is not None and ex.need_dmod
+        dmod = ws.dmod if want_mod else None
+        if want_mod:
+            dmod.zero_()
+        if ex is not None and ex.hidden[b] is not None:
+            ex.d_hidden[b] = dx.float().sum(0)
+
+        # ---- FFN
+        ops.gate_mul(ws.g1, dx, gate_mlp, tokens_per_frame=tpf, branch=ws.branch_m if want_mod else None,
+                     dgate_acc=dmod[:, 5 * C:6 * C] if want_mod else None)
+        s1, s3, s2 = st["w1"], st["w3"], st["w2"]
+        if s1.has_lora or s3.has_lora:
+            self._linear_bwd(s2, ws.g1, ws.h, ops.epi(ops.EPI_STORE, ws.h), "w2")      # dh overwrites h (h no longer needed)
+            ops.swiglu_bwd(ws.dh1, ws.dh3, ws.h, ws.h1, ws.h3)
+            self._linear_bwd(s1, ws.dh1, ws.xm2, ops.epi(ops.EPI_STORE, ws.g2), "w1")
+            self._linear_bwd(s3, ws.dh3, ws.xm2, ops.epi(ops.EPI_STORE, ws.g1), "w3")
+            ws.g2.add_(ws.g1)
+        else:
+            self._linear_bwd(s2, ws.g1, ws.h, ops.epi(ops.EPI_SWIGLU_BWD, ws.dh1, d2=ws.dh3, aux1=ws.h1, aux2=ws.h3), "w2")
+            ops.gemm(N, C, [(ws.dh1, s1.W, self.F, True, None), (ws.dh3, s3.W, self.F, True, None)],
+                     ops.epi(ops.EPI_STORE, ws.g2))
+        ops.ln_mod_bwd(dx, ws.g2, ws.x2, scale_mlp, dx_resid=dx, tokens_per_frame=tpf,
+                       dscale_acc=dmod[:, 4 * C:5 * C] if want_mod else None,
+                       dshift_acc=dmod[:, 3 * C:4 * C] if want_mod else None)
+        # ---- cross attention
+        if Nn > 0:
+            dxn = dx[Nc:]
+            s = st["cproj"]
+            self._linear_bwd(s, dxn, ws.oc, ops.epi(ops.EPI_STORE, ws.g1[:Nn]), "cproj")          # dOc
+            vc = ws.kvc.view(M, 2 * H, D)[:, H:]
+            dkc = ws.dkvc.view(M, 2 * H, D)[:, :H]
+            dvc = ws.dkvc.view(M, 2 * H, D)[:, H:]
+            ops.attn_bwd(ws.dqc.view(Nn, H, D), dkc, dvc, ws.g1[:Nn].view(Nn, H, D), ws.oc.view(Nn, H, D), ws.lsec,
+                         ws.deltac, ws.qcn.view(Nn, H, D), ws.kcn.view(M, H, D), vc, [(0, Nn, M)], self.softmax_scale)
+            ng = ex is not None and ex.norm_grads
+            cq, ck = blk.cross_attn.q_norm.weight, blk.cross_attn.k_norm.weight
+            ops.qk_rmsnorm_rope_bwd(ws.dqc, ws.dqc, ws.qc, cq, None, H, 0, rope=False,
+                                    dwq_acc=self._ngrad(ex, b, "cross_attn.q_norm.weight", cq) if ng else None)
+            ops.qk_rmsnorm_rope_bwd(ws.dkvc[:, :C], ws.dkvc[:, :C], ws.kvc[:, :C], ck, None, H, 0, rope=False,
+                                    dwq_acc=self._ngrad(ex, b, "cross_attn.k_norm.weight", ck) if ng else None)
+            self._linear_bwd(st["kv_linear"], ws.dkvc, ws.y, None, "kv_linear")                    # adapter grads only
+            s = st["q_linear"]
+            self._linear_bwd(s, ws.dqc, ws.xn, ops.epi(ops.EPI_STORE, ws.g2[:Nn]), "q_linear")    # d xn
+            nrm = blk.pre_crs_attn_norm
+            ops.ln_mod_bwd(dxn, ws.g2[:Nn], ws.x1[Nc:], nrm.weight, dx_resid=dxn, tokens_per_frame=tpf, affine=True,
+                           dscale_acc=self._ngrad(ex, b, "pre_crs_attn_norm.weight", nrm.weight) if ng else None,
+                           dshift_acc=self._ngrad(ex, b, "pre_crs_attn_norm.bias", nrm.bias) if ng else None)
+        # ---- self attention
+        ops.gate_mul(ws.g1, dx, gate_msa, tokens_per_frame=tpf, branch=ws.branch_a if want_mod else None,
+                     dgate_acc=dmod[:, 2 * C:3 * C] if want_mod else None)
+        s = st["proj"]
+        self._linear_bwd(s, ws.g1, ws.o, ops.epi(ops.EPI_STORE, ws.g2), "proj")                   # dO
+        q = ws.qk.view(N, 2 * H, D)[:, :H]
+        k = ws.qk.view(N, 2 * H, D)[:, H:]
+        v = ws.qkv.view(N, 3 * H, D)[:, 2 * H:]
+        dq = ws.dqk.view(N, 2 * H, D)[:, :H]
+        dk = ws.dqk.view(N, 2 * H, D)[:, H:]
+        dv = ws.dqkv.view(N, 3 * H, D)[:, 2 * H:]
+        ops.attn_bwd(dq, dk, dv, ws.g2.view(N, H, D), ws.o.view(N, H, D), ws.lse, ws.delta, q, k, v,
+                     geo.self_segments(), self.softmax_scale)
+        ng = ex is not None and ex.norm_grads
+        ops.qk_rmsnorm_rope_bwd(ws.dqkv, ws.dqk, ws.qkv, blk.attn.q_norm.weight, blk.attn.k_norm.weight, H, H,
+                                grid_hw=(geo.gh, geo.gw), rope_base=self.dit.config.rope_base,
+                                dwq_acc=self._ngrad(ex, b, "attn.q_norm.weight", blk.attn.q_norm.weight) if ng else None,
+                                dwk_acc=self._ngrad(ex, b, "attn.k_norm.weight", blk.attn.k_norm.weight) if ng else None)
+        s = st["qkv"]
+        self._linear_bwd(s, ws.dqkv, ws.xm1, ops.epi(ops.EPI_STORE, ws.g1), "qkv")                # d xm1
+        ops.ln_mod_bwd(dx, ws.g1, x_in, scale_msa, dx_resid=dx, tokens_per_frame=tpf,
+                       dscale_acc=dmod[:, C:2 * C] if want_mod else None,
+                       dshift_acc=dmod[:, 0:C] if want_mod else None)
+        if want_mod:
+            ex.d_mod[b] = dmod.clone()
+            if ex.need_dt:
+                ada = blk.adaLN_modulation[1]
+                ops.skinny_linear_bwd(ws.dt, dmod, self._t_for_block(b, ex), ada.weight, act=1)
+                ex.d_t[b] = ws.dt.clone()
+
+    @staticmethod
+    def _ngrad(ex: Extras, b: int, name: str, like: torch.Tensor):
+        key = f"blocks.{b}.{name}"
+        if key not in ex.d_norm:
+            ex.d_norm[key] = torch.zeros(like.numel(), dtype=F32, device=like.device)
+        return ex.d_norm[key]
+
+    # ------------------------------------------------------------------ whole network
+    def _prepare(self, geo: Geometry, ex: Optional[Extras]):
+        self.resolve_sites()
+        self.plan(geo)
+        for s in self.lora_sites():
+            s.refresh()
+        if ex is not None and ex.need_dmod and self.ws.branch_a is None:
+            self.ws.branch_a = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
+            self.ws.branch_m = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
+
+    def forward_tokens(self, text_valid: torch.Tensor, ex: Optional[Extras] = None) -> torch.Tensor:
+        """ws.P / ws.timestep must hold the patchified input and the per-frame timestep.  Returns ws.pred [N,64] f32
+        (final-layer token layout) and leaves the block inputs in ws.xs for the backward."""
+        ws, geo, C = self.ws, self.geo, self.C
+        pe = self.dit.x_embedder.proj
+        ops.gemm(geo.N, C, [(ws.P, pe.weight.view(C, 64), 64, False, None)], ops.epi(ops.EPI_STORE, ws.xs[0], bias=pe.bias))
+        self._embed_time()
+        self._embed_text(text_valid)
+        for b in range(self.L):
+            self._block_fwd(b, ws.xs[b], ws.xs[b + 1], ex)
+        x_last = ws.xs[self.L]
+        if ex is not None and ex.hidden_final is not None:
+            x_last.add_(ex.hidden_final.to(BF16)[None, :])
+        fl = self.dit.final_layer
+        t_f = ws.t
+        if ex is not None and ex.t_offset_final is not None:
+            t_f = torch.add(ws.t, ex.t_offset_final.to(F32)[None, :], out=ws.t_blk)
+        ops.skinny_linear(ws.modf, t_f, fl.adaLN_modulation[1].weight, fl.adaLN_modulation[1].bias, act=1)
+        ops.ln_mod_fwd(ws.xf, x_last, ws.modf[:, C:], ws.modf[:, :C], tokens_per_frame=geo.tpf)
+        ops.gemm(geo.N, 64, [(ws.xf, fl.linear.weight, C, False, None)], ops.epi(ops.EPI_STORE_F32, ws.pred, bias=fl.linear.bias))
+        if ex is not None and ex.out_bias is not None:
+            ws.pred.view(geo.N, 4, 16).add_(ex.out_bias.to(F32)[None, None, :])
+        return ws.pred
+
+    def backward_tokens(self, ex: Optional[Extras] = None, only_out_bias: bool = False):
+        """ws.dpred [Nn, 64] bf16 holds d loss / d pred for the noise rows (context rows carry no loss)."""
+        ws, geo, C = self.ws, self.geo, self.C
+        fl = self.dit.final_layer
+        if ex is not None and ex.out_bias is not None:
+            ex.d_out_bias = ws.dpred.float().view(-1, 4, 16).sum((0, 1))
+            if only_out_bias:
+                return
+        self.grad_flat.zero_()
+        # final layer: d xf = dpred W_lin ; context rows are zero
+        ws.g1[: geo.Nc].zero_()
+        ops.gemm(geo.Nn, C, [(ws.dpred, fl.linear.weight, 64, True, None)], ops.epi(ops.EPI_STORE, ws.g1[geo.Nc:]))
+        want_mod = ex is not None and ex.need_dmod
+        if want_mod:
+            ws.dmodf.zero_()
+        ops.ln_mod_bwd(ws.dx, ws.g1, ws.xs[self.L], ws.modf[:, C:], tokens_per_frame=geo.tpf,
+                       dscale_acc=ws.dmodf[:, C:] if want_mod else None, dshift_acc=ws.dmodf[:, :C] if want_mod else None)
+        if want_mod and ex.need_dt:
+            t_f = ws.t
+            if ex.t_offset_final is not None:
+                t_f = torch.add(ws.t, ex.t_offset_final.to(F32)[None, :], out=ws.t_blk)
+            ops.skinny_linear_bwd(ws.dt, ws.dmodf, t_f, fl.adaLN_modulation[1].weight, act=1)
+            ex.d_t_final = ws.dt.clone()
+        if ex is not None and ex.hidden_final is not None:
+            ex.d_hidden_final = ws.dx.float().sum(0)
+        for b in reversed(range(self.L)):
+            if getattr(self, "_ws_holds", None) != b:  # the last block's intermediates are still in the workspace
+                self._block_fwd(b, ws.xs[b], ws.g2, ex)   # recompute (block output discarded into g2)
+            self._block_bwd(b, ws.xs[b], ex)
+        self._ws_holds = None
+
+    # ------------------------------------------------------------------ step-level helpers
+    def set_inputs(self, cond, target, noise, sigma):
+        """cond [16,Tc,H,W], target/noise [16,Tt,H,W] bf16, sigma f32 [1] (device).  Fills ws.P / ws.V / ws.timestep."""
+        ops.noise_patchify(self.ws.P, self.ws.V, self.ws.timestep, cond, target, noise, sigma)
+
+    def loss_and_dpred(self, want_grad: bool = True, loss_scale: float = 1.0) -> torch.Tensor:
+        ws, geo = self.ws, self.geo
+        ws.loss.zero_()
+        ops.mse_fwd_bwd(ws.loss, ws.dpred if want_grad else None, ws.pred[geo.Nc:], ws.V, loss_scale=loss_scale)
+        return ws.loss
+
+
+# ---------------------------------------------------------------------------------------------------- autograd entry
+def _geometry_for(dit, hidden_states, n_cond, M) -> Geometry:
+    B, Cin, T, Hl, Wl = hidden_states.shape
+    if B != 1:
+        raise NotImplementedError("batch size 1 only (as in every reference run: common.py:448, run_sweep.sbatch:8)")
+    return Geometry(T=T, Hl=Hl, Wl=Wl, n_cond=int(n_cond), M=M)
+
+
+class _DiTFunction(torch.autograd.Function):
+    """pred = dit(hidden, timestep, text) with gradients for the adapter parameters only."""
+
+    @staticmethod
+    def forward(ctx, dit, hidden_states, timestep, text_valid, n_cond, *params):
+        eng = dit.engine
+        geo = _geometry_for(dit, hidden_states, n_cond, text_valid.shape[0])
+        eng._prepare(geo, None)
+        ws = eng.ws
+        ops.noise_patchify(ws.P, None, None, hidden_states[0].to(BF16).contiguous(), None, None, None)
+        ws.timestep.copy_(timestep.reshape(-1).to(BF16).float())  # the DiT re-casts the timestep to its dtype first
+        eng.forward_tokens(text_valid)
+        out = torch.empty(1, 16, geo.T, geo.Hl, geo.Wl, dtype=F32, device=eng.device)
+        ops.unpatchify(out[0], ws.pred, geo.T, geo.Hl, geo.Wl)
+        ctx.dit, ctx.geo, ctx.text_valid = dit, geo, text_valid
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        eng, geo = ctx.dit.engine, ctx.geo
+        if eng.geo != geo:
+            raise RuntimeError("the engine workspace was re-planned between forward and backward")
+        ws = eng.ws
+        # d pred on context frames is dropped: the loss never touches them (common.py:485) -- checked here
+        g = grad_out[0].contiguous().float()
+        if geo.n_cond > 0 and bool((g[:, : geo.n_cond] != 0).any()):
+            raise NotImplementedError("gradient flowing into context-frame predictions is not supported")
+        ops.latent_to_tokens(ws.dpred, g, geo.T, geo.Hl, geo.Wl, geo.n_cond)
+        eng.backward_tokens(None)
+        grads = []
+        for s in eng.lora_sites():
+            for p, gr in zip(s.params, s.param_grads()):
+                grads.append(gr.to(p.dtype).contiguous() if p.requires_grad else None)
+        assert len(grads) == ctx.n_params
+        return (None, None, None, None, None, *grads)
+
+
+def dit_forward_autograd(dit, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask, num_cond_latents):
+    if not hidden_states.is_cuda:
+        from ._lib import B200TTAError
+        raise B200TTAError("B200DiT runs on a B200 only: inputs are on %s and there is no CPU fallback" % hidden_states.device)
+    eng = dit.engine
+    text_valid = eng.pack_text(encoder_hidden_states, encoder_attention_mask)
+    if timestep.dim() == 1:
+        timestep = timestep.unsqueeze(1).expand(-1, hidden_states.shape[2])
+    params = eng.adapter_parameters()
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _DiTFunction.apply(dit, hidden_states, timestep, text_valid, num_cond_latents, *params)
+    with torch.no_grad():
+        return _DiTFunction.forward(_NoCtx(), dit, hidden_states, timestep, text_valid, num_cond_latents, *params)
+
+
+class _NoCtx:
+    pass

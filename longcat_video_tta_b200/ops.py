@@ -182,6 +182,18 @@ def unpatchify(latent, tokens, T: int, H: int, W: int):
     _call("b200tta_unpatchify", _p(latent), _p(tokens), T, H, W, _stream())
 
 
+def latent_to_tokens(tokens, latent, T: int, H: int, W: int, t_begin: int = 0):
+    _call("b200tta_latent_to_tokens", _p(tokens), _p(latent), T, H, W, t_begin, _stream())
+
+
+def swiglu_fwd(h, h1, h3):
+    _call("b200tta_swiglu_fwd", _p(h), _p(h1), _p(h3), h.numel(), _stream())
+
+
+def swiglu_bwd(dh1, dh3, dh, h1, h3):
+    _call("b200tta_swiglu_bwd", _p(dh1), _p(dh3), _p(dh), _p(h1), _p(h3), dh.numel(), _stream())
+
+
 def mse_fwd_bwd(loss, dpred, pred, V, *, loss_scale: float = 1.0):
     _call("b200tta_mse_fwd_bwd", _p(loss), _p(dpred), _p(pred), _p(V), pred.numel(), float(loss_scale), _stream())
 

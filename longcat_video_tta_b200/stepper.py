@@ -1,0 +1,164 @@
+"""TTAStepper: one fused flow-matching TTA update (noise -> forward -> adapter backward -> clip -> AdamW).
+
+This is the hot loop body of ``finetune_lora_on_conditioning`` (lora_experiment/scripts/run_lora_tta.py:490-516)
+and of the ``optimize_*`` loops of the delta / norm / FiLM methods, executed without autograd: the random draws stay
+in PyTorch (bit-exact RNG stream, SURVEY 7 "RNG parity"), everything else is hand-written kernels.
+
+Data-parallel mode (SURVEY 8e -- our extension, the reference is single-GPU): every rank holds the frozen backbone
+and a replica of the adapters, processes its own (sigma, eps) draw, and the flat fp32 adapter-gradient buffer is
+all-reduced once per step with NCCL; the 1/world scale is folded into the clip / AdamW kernels.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .engine import Extras, Geometry, TTAEngine
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+class ParamGroup:
+    """A set of trainable tensors with one clip policy and its own device descriptor table."""
+
+    def __init__(self, entries: List[dict], device, per_tensor_clip: bool = False):
+        self.entries = entries
+        self.per_tensor_clip = per_tensor_clip
+        self.tl = ops.TensorList(entries, device) if entries else None
+
+
+def _state_like(p: torch.Tensor, fp32: bool):
+    return torch.zeros(p.shape, dtype=F32 if fp32 else p.dtype, device=p.device)
+
+
+class TTAStepper:
+    def __init__(self, dit, *, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
+                 max_grad_norm: float = 1.0, per_tensor_clip: bool = False, master_weights: bool = True,
+                 faithful_bf16: bool = False, extra_params: Optional[Sequence[torch.nn.Parameter]] = None,
+                 extras: Optional[Extras] = None, extra_grad_fn=None, train_lora: bool = True, process_group=None):
+        """
+        master_weights : keep an fp32 master copy (and fp32 Adam moments) of every bf16 adapter tensor.  The
+                         reference keeps params and moments in bf16 (run_lora_tta.py:332) where updates below half an
+                         ulp are lost; ``faithful_bf16=True, master_weights=False`` reproduces
+                         that op-by-op rounding instead.
+        extra_params   : non-LoRA trainables (delta vectors, FiLM corrections, norm weights ...); ``extra_grad_fn(ex)``
+                         returns their fp32 gradients (same order) after the backward.
+        """
+        self.dit = dit
+        self.eng: TTAEngine = dit.engine
+        self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
+        self.faithful = faithful_bf16
+        self.extras = extras
+        self.extra_grad_fn = extra_grad_fn
+        self.extra_params = list(extra_params or [])
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.step_count = 0
+        dev = self.eng.device
+        self.eng.resolve_sites()
+        entries, self._staged = [], []
+        if train_lora:
+            for s in self.eng.lora_sites():
+                grads = [s.dA_acc, s.dB_acc] if not s.staged else [None] * len(s.params)
+                for i, p in enumerate(s.params):
+                    use_master = master_weights and p.dtype == BF16
+                    fp32_state = use_master or p.dtype == F32
+                    e = dict(param=p.data, exp_avg=_state_like(p, fp32_state), exp_avg_sq=_state_like(p, fp32_state))
+                    if use_master:
+                        e["master"] = p.data.float()
+                    if s.staged:
+                        e["grad"] = torch.zeros(p.shape, dtype=F32, device=dev)
+                    else:
+                        e["grad"] = grads[i]
+                        e["grad_transposed"] = i == 0  # dA is accumulated as [in, r]
+                    entries.append(e)
+                if s.staged:
+                    self._staged.append((s, entries[-len(s.params):]))
+        self._n_lora_entries = len(entries)
+        self._extra_entries = []
+        for p in self.extra_params:
+            use_master = master_weights and p.dtype == BF16
+            fp32_state = use_master or p.dtype == F32
+            e = dict(param=p.data, grad=torch.zeros(p.shape, dtype=F32, device=dev),
+                     exp_avg=_state_like(p, fp32_state), exp_avg_sq=_state_like(p, fp32_state))
+            if use_master:
+                e["master"] = p.data.float()
+            self._extra_entries.append(e)
+        self.group = ParamGroup(entries + self._extra_entries, dev, per_tensor_clip)
+        self.n_params = sum(e["param"].numel() for e in self.group.entries)
+
+    # ------------------------------------------------------------------
+    def _geometry(self, cond, target, text_valid) -> Geometry:
+        B, _, Tc, Hl, Wl = cond.shape
+        if B != 1:
+            raise NotImplementedError("batch size 1 only (every reference run; common.py:448)")
+        return Geometry(T=Tc + target.shape[2], Hl=Hl, Wl=Wl, n_cond=Tc, M=text_valid.shape[0])
+
+    def forward_backward(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
+        """Loss (device scalar, f32) and adapter gradients for explicit (sigma, eps)."""
+        eng = self.eng
+        text_valid = eng.pack_text(prompt_embeds, prompt_mask)
+        geo = self._geometry(cond, target, text_valid)
+        ex = self.extras
+        eng._prepare(geo, ex)
+        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
+        eng.forward_tokens(text_valid, ex)
+        loss = eng.loss_and_dpred(True)
+        only_bias = ex is not None and ex.out_bias is not None and not self._needs_dit_backward()
+        eng.backward_tokens(ex, only_out_bias=only_bias)
+        return loss
+
+    def _needs_dit_backward(self) -> bool:
+        if self._n_lora_entries > 0:
+            return True
+        ex = self.extras
+        if ex is None:
+            return False
+        return (ex.need_dmod or ex.norm_grads or any(h is not None for h in ex.hidden) or ex.hidden_final is not None)
+
+    def _sync_grads(self):
+        if self.world > 1:
+            bufs = [self.eng.grad_flat] + [e["grad"] for e in self._extra_entries]
+            for b in bufs:
+                torch.distributed.all_reduce(b, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self, lr: float):
+        self.step_count += 1
+        if self.extra_grad_fn is not None and self._extra_entries:
+            for e, g in zip(self._extra_entries, self.extra_grad_fn(self.extras)):
+                e["grad"].copy_(g.reshape(e["grad"].shape))
+        self._sync_grads()
+        for s, ents in self._staged:
+            for e, g in zip(ents, s.param_grads()):
+                e["grad"].copy_(g)
+        tl = self.group.tl
+        gs = 1.0 / self.world
+        if self.max_norm is not None and self.max_norm > 0:
+            tl.clip_coef(self.max_norm, per_tensor=self.group.per_tensor_clip, grad_scale=gs)
+        tl.adamw(lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, step=self.step_count, grad_scale=gs,
+                 use_coef=self.max_norm is not None and self.max_norm > 0, faithful_bf16=self.faithful)
+
+    def step(self, cond, target, prompt_embeds, prompt_mask, sigma, noise, lr: float) -> torch.Tensor:
+        loss = self.forward_backward(cond, target, prompt_embeds, prompt_mask, sigma, noise)
+        out = loss.clone()
+        self.optimizer_step(lr)
+        return out
+
+    # ------------------------------------------------------------------ forward-only (anchor loss, common.py:492-559)
+    @torch.no_grad()
+    def eval_loss(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
+        eng = self.eng
+        text_valid = eng.pack_text(prompt_embeds, prompt_mask)
+        geo = self._geometry(cond, target, text_valid)
+        eng._prepare(geo, self.extras)
+        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
+        eng.forward_tokens(text_valid, self.extras)
+        eng._ws_holds = None
+        return eng.loss_and_dpred(False).clone()
+
+    def total_grad_norm(self) -> torch.Tensor:
+        return self.group.tl.total_norm
