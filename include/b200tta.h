@@ -33,6 +33,8 @@ extern "C" {
 typedef void* b200tta_stream_t; /* cudaStream_t */
 
 int b200tta_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+int64_t b200tta_launch_count(void);
 const char* b200tta_last_error(void);
 /* Returns 0 on an sm_100 device after running a tiny tcgen05 GEMM against a CUDA-core
  * reference on device; B200TTA_EARCH elsewhere. */

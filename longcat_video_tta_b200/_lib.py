@@ -87,6 +87,8 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError here == header / library mismatch
             fn.argtypes = argtypes
             fn.restype = i32
+        lib.b200tta_launch_count.argtypes = []
+        lib.b200tta_launch_count.restype = i64
         lib.b200tta_last_error.argtypes = []
         lib.b200tta_last_error.restype = C.c_char_p
         _lib = lib

@@ -442,11 +442,11 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
         const long long warps = (long long)n_q * heads;
         delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(delta, (const __nv_bfloat16*)dO, lddo,
                                                                           (const __nv_bfloat16*)O, ldo, n_q, heads);
-        B200_CUDA(cudaGetLastError());
+        B200_LAUNCHED();
     }
     dq_kernel<<<dim3(items, heads), NUM_THREADS, SMEM_BYTES, st>>>(p);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     dkv_kernel<<<dim3((n_kv + BT - 1) / BT, heads), NUM_THREADS, SMEM_BYTES, st>>>(p);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -315,6 +315,6 @@ extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q,
         attr = true;
     }
     attn_fwd_kernel<<<dim3(items, heads), NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -618,7 +618,7 @@ extern "C" int b200tta_ln_mod_fwd(void* Y, int64_t ldy, const void* X, int64_t l
     LN_DISPATCH(C / 256, (ln_mod_fwd_kernel<CH><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(
                              (__nv_bfloat16*)Y, ldy, (const __nv_bfloat16*)X, ldx, scale, shift, mod_ld, params_bf16,
                              mul_base, rows, tokens_per_frame, eps)));
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -646,7 +646,7 @@ extern "C" int b200tta_ln_mod_bwd(void* dX, int64_t lddx, const void* dX_resid, 
             (__nv_bfloat16*)dX, lddx, (const __nv_bfloat16*)dX_resid, ldr, (const __nv_bfloat16*)dY, lddy,
             (const __nv_bfloat16*)X, ldx, scale, mod_ld, params_bf16, mul_base, rows, C, tokens_per_frame, eps);
     }
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     if (dscale_acc || dshift_acc) {
         // affine form (mod_ld == 0): every row belongs to "frame" 0 -> treat the whole input as one frame
         const long long tpf = mod_ld == 0 ? rows : tokens_per_frame;
@@ -656,7 +656,7 @@ extern "C" int b200tta_ln_mod_bwd(void* dX, int64_t lddx, const void* dX_resid, 
         LN_DISPATCH(C / 256, (ln_param_grad_kernel<CH><<<g, WARPS_PER_BLOCK * 32, smem, st>>>(
                                  (const __nv_bfloat16*)dY, lddy, (const __nv_bfloat16*)X, ldx, dscale_acc, dshift_acc,
                                  acc_ld, rows, (int)tpf, eps)));
-        B200_CUDA(cudaGetLastError());
+        B200_LAUNCHED();
     }
     return B200TTA_OK;
 }
@@ -673,7 +673,7 @@ extern "C" int b200tta_qk_rmsnorm_rope_fwd(void* Y, int64_t ldy, const void* X, 
     qk_norm_rope_fwd_kernel<<<grid, WARPS_PER_BLOCK * 32, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)Y, ldy, (const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)wq, (const __nv_bfloat16*)wk,
         n_q_slots, n_k_slots, rows, row_offset, grid_h, grid_w, rope, rope_base, eps);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -691,7 +691,7 @@ extern "C" int b200tta_qk_rmsnorm_rope_bwd(void* dX, int64_t lddx, const void* d
         (__nv_bfloat16*)dX, lddx, (const __nv_bfloat16*)dY, lddy, (const __nv_bfloat16*)X, ldx,
         (const __nv_bfloat16*)wq, (const __nv_bfloat16*)wk, dwq_acc, dwk_acc, n_q_slots, n_k_slots, rows, row_offset,
         grid_h, grid_w, rope, rope_base, eps);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -705,14 +705,14 @@ extern "C" int b200tta_gate_mul(void* dY, int64_t lddy, const void* dX, int64_t 
     cudaStream_t st = (cudaStream_t)stream;
     gate_mul_kernel<<<grid_for(rows * (C / 8), 256), 256, 0, st>>>((__nv_bfloat16*)dY, lddy, (const __nv_bfloat16*)dX,
                                                                    lddx, gate, ldg, rows, C, tokens_per_frame);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     if (dgate_acc) {
         B200_REQUIRE(branch != nullptr, "gate_mul: dgate_acc needs the branch output");
         const int rpb = 128;
         dim3 g((C + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
         colsum_prod_kernel<<<g, 256, 0, st>>>(dgate_acc, acc_ld, (const __nv_bfloat16*)dX, lddx,
                                               (const __nv_bfloat16*)branch, ldb, rows, C, tokens_per_frame, rpb);
-        B200_CUDA(cudaGetLastError());
+        B200_LAUNCHED();
     }
     return B200TTA_OK;
 }
@@ -728,7 +728,7 @@ extern "C" int b200tta_noise_patchify(void* P, float* V, float* timestep, const 
     noise_patchify_kernel<<<grid_for(n_tok * 16, 256), 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)P, V, timestep, (const __nv_bfloat16*)cond, (const __nv_bfloat16*)target,
         (const __nv_bfloat16*)noise, sigma, t_cond, t_tgt, H, W, num_train_timesteps);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -741,7 +741,7 @@ extern "C" int b200tta_unpatchify(float* latent, const float* tokens, int32_t T,
     if (int rc = require_sm100()) return rc;
     B200_REQUIRE(latent && tokens && T > 0 && H % 2 == 0 && W % 2 == 0, "unpatchify: bad arguments");
     unpatchify_kernel<<<grid_for((long long)16 * T * H * W, 256), 256, 0, (cudaStream_t)stream>>>(latent, tokens, T, H, W);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -751,7 +751,7 @@ extern "C" int b200tta_mse_fwd_bwd(float* loss, void* dpred, const float* pred, 
     B200_REQUIRE(loss && pred && V && n > 0 && n % 4 == 0 && aligned16(pred) && aligned16(V), "mse_fwd_bwd: bad arguments");
     mse_kernel<<<grid_for(n / 4, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(loss, (__nv_bfloat16*)dpred, pred, V, n,
                                                                                1.0f / (float)n, loss_scale);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -761,7 +761,7 @@ extern "C" int b200tta_timestep_sinusoid(float* F, const float* timestep, int32_
     B200_REQUIRE(F && timestep && rows > 0 && dim > 0 && dim % 2 == 0, "timestep_sinusoid: bad arguments");
     const int n = rows * dim / 2;
     sinusoid_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(F, timestep, rows, dim);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -781,7 +781,7 @@ extern "C" int b200tta_skinny_linear(float* Y, const float* X, const void* W, co
     if (grid > 148 * 4) grid = 148 * 4;
     skinny_linear_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(Y, X, W, bias, addend, w_bf16, R, in_features,
                                                                     out_features, act);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -802,7 +802,7 @@ extern "C" int b200tta_skinny_linear_bwd(float* dX, const float* dY, const float
     }
     skinny_linear_bwd_kernel<<<g, 256, smem, st>>>(dX, dY, X, W, w_bf16, R, in_features, out_features, act, accumulate,
                                                    out_chunk);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -811,7 +811,7 @@ extern "C" int b200tta_swiglu_fwd(void* Hout, const void* H1, const void* H3, in
     B200_REQUIRE(Hout && H1 && H3 && n > 0 && n % 8 == 0 && aligned16(Hout) && aligned16(H1) && aligned16(H3), "swiglu_fwd: bad arguments");
     swiglu_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)Hout, (const __nv_bfloat16*)H1,
                                                                               (const __nv_bfloat16*)H3, n / 8);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -822,7 +822,7 @@ extern "C" int b200tta_swiglu_bwd(void* dH1, void* dH3, const void* dH, const vo
                      aligned16(H1) && aligned16(H3), "swiglu_bwd: bad arguments");
     swiglu_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)dH1, (__nv_bfloat16*)dH3, (const __nv_bfloat16*)dH, (const __nv_bfloat16*)H1, (const __nv_bfloat16*)H3, n / 8);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -832,6 +832,6 @@ extern "C" int b200tta_latent_to_tokens(void* tokens, const float* latent, int32
     B200_REQUIRE(tokens && latent && T > 0 && t_begin >= 0 && t_begin < T && H % 2 == 0 && W % 2 == 0, "latent_to_tokens: bad arguments");
     const long long total = (long long)(T - t_begin) * (H / 2) * (W / 2) * 64;
     latent_to_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)tokens, latent, T, H, W, t_begin);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -359,7 +359,7 @@ int launch(const GemmParams& p, cudaStream_t stream) {
     const int tiles = p.m_tiles * p.n_tiles;
     const int grid = tiles < sm_count() ? tiles : sm_count();
     gemm_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(p);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 

@@ -1,6 +1,7 @@
 // Error reporting, device checks and TMA tensor-map encoding for libb200tta.so.
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
@@ -39,6 +40,10 @@ int require_sm100() {
     }
     return B200TTA_OK;
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() { return g_sm_count > 0 ? g_sm_count : 148; }
 
@@ -98,5 +103,7 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
 
 }  // namespace b200
 
+namespace b200 { unsigned long long launches(); }
 extern "C" int b200tta_version(void) { return 100; }
+extern "C" int64_t b200tta_launch_count(void) { return (int64_t)b200::launches(); }
 extern "C" const char* b200tta_last_error(void) { return b200::g_err; }

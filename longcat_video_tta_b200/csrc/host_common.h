@@ -22,6 +22,13 @@ void set_last_error(const char* fmt, ...);
         }                                       \
     } while (0)
 
+// use right after a <<<>>> launch: counts it and surfaces launch errors
+#define B200_LAUNCHED()                   \
+    do {                                  \
+        b200::count_launch(1);            \
+        B200_CUDA(cudaGetLastError());    \
+    } while (0)
+
 #define B200_CUDA(call)                                                                        \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \
@@ -30,6 +37,9 @@ void set_last_error(const char* fmt, ...);
             return B200TTA_ECUDA;                                                              \
         }                                                                                      \
     } while (0)
+
+// process-wide count of kernels this library has launched (b200tta_launch_count)
+void count_launch(int n = 1);
 
 // returns 0 when the current device is sm_100 (B200); EARCH otherwise.  Cached per process.
 int require_sm100();

@@ -219,7 +219,7 @@ extern "C" int b200tta_lora_down(void* T, int64_t ldt, const void* X, int64_t ld
     NT_DISPATCH(rp, (lora_down_kernel<NT><<<grid, DN_THREADS, 0, (cudaStream_t)stream>>>(
                         (__nv_bfloat16*)T, ldt, (const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)Wd, wd_t, n_tok, k, r,
                         scale)));
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -239,7 +239,7 @@ extern "C" int b200tta_lora_grad(float* G, const void* P, int64_t ldp, const voi
     dim3 grid(mt, (unsigned)((n_tok + tps - 1) / tps));
     NT_DISPATCH(r, (lora_grad_kernel<NT><<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>(
                        G, (const __nv_bfloat16*)P, ldp, (const __nv_bfloat16*)Q, ldq, n_tok, m, r, tps)));
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 

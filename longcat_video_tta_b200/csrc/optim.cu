@@ -140,7 +140,7 @@ extern "C" int b200tta_mt_sumsq(const b200tta_tensor_desc* descs_dev, int32_t n,
     if (int rc = require_sm100()) return rc;
     B200_REQUIRE(descs_dev && sumsq && n > 0 && n <= 65535 && max_numel > 0, "mt_sumsq: bad arguments (n=%d)", n);
     sumsq_kernel<<<opt_grid(n, max_numel), OPT_THREADS, 0, (cudaStream_t)stream>>>(descs_dev, sumsq);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -149,7 +149,7 @@ extern "C" int b200tta_clip_coef(float* coef, float* total_norm_out, const float
     if (int rc = require_sm100()) return rc;
     B200_REQUIRE(coef && sumsq && n > 0, "clip_coef: bad arguments");
     clip_coef_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(coef, total_norm_out, sumsq, n, max_norm, per_tensor, grad_scale);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 
@@ -164,6 +164,6 @@ extern "C" int b200tta_mt_adamw(const b200tta_tensor_desc* descs_dev, int32_t n,
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.faithful_bf16 = faithful_bf16;
     adamw_kernel<<<opt_grid(n, max_numel), OPT_THREADS, 0, (cudaStream_t)stream>>>(descs_dev, coef, a);
-    B200_CUDA(cudaGetLastError());
+    B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -337,19 +337,31 @@ class TTAEngine:
 
     # ------------------------------------------------------------------ text / time embeddings
     def pack_text(self, prompt_embeds: torch.Tensor, mask: Optional[torch.Tensor]) -> torch.Tensor:
-        """[B=1,1,Ltxt,Cc] (+ mask [1,Ltxt]) -> valid rows [M, Cc] bf16 (run_delta_a.py:170-192: y_embedder is
-        row-wise, so packing the valid tokens before or after it is the same arithmetic)."""
+        """[B=1,1,Ltxt,Cc] (+ mask [1,Ltxt]) -> text rows [M, Cc] bf16 fed to y_embedder (run_delta_a.py:170-192).
+
+        text_tokens_zero_pad = True  : every token stays a key/value; rows of padded tokens are ZEROED after
+                                       y_embedder (the reference multiplies by the mask, then resets the mask to ones),
+                                       so M = Ltxt and ``self._text_keep`` holds the 0/1 row mask;
+        text_tokens_zero_pad = False : only valid tokens are packed (y_embedder is row-wise, so packing before or
+                                       after it is the same arithmetic), M = mask.sum().
+        """
         key = (prompt_embeds.data_ptr(), prompt_embeds._version, None if mask is None else (mask.data_ptr(), mask._version))
         if self._text_cache is not None and self._text_cache[0] == key:
+            self._text_keep = self._text_cache[2]
             return self._text_cache[1]
-        pe = prompt_embeds.reshape(-1, prompt_embeds.shape[-1])
         if prompt_embeds.shape[0] != 1:
             raise NotImplementedError("batch size 1 only (as in every reference run)")
+        pe = prompt_embeds.reshape(-1, prompt_embeds.shape[-1])
+        keep = None
         if mask is not None:
-            idx = mask.reshape(-1).nonzero(as_tuple=False).flatten()
-            pe = pe.index_select(0, idx.to(pe.device))
+            if self.dit.text_tokens_zero_pad:
+                keep = (mask.reshape(-1) != 0).to(device=self.device, dtype=BF16)[:, None].contiguous()
+            else:
+                idx = mask.reshape(-1).nonzero(as_tuple=False).flatten()
+                pe = pe.index_select(0, idx.to(pe.device))
         pe = pe.to(device=self.device, dtype=BF16).contiguous()
-        self._text_cache = (key, pe)
+        self._text_cache = (key, pe, keep)
+        self._text_keep = keep
         return pe
 
     def _embed_text(self, text_valid):
@@ -358,6 +370,8 @@ class TTAEngine:
         ops.gemm(M, self.C, [(text_valid, ye[0].weight, text_valid.shape[1], False, None)],
                  ops.epi(ops.EPI_GELU, ws.y1, bias=ye[0].bias))
         ops.gemm(M, self.C, [(ws.y1, ye[2].weight, self.C, False, None)], ops.epi(ops.EPI_STORE, ws.y, bias=ye[2].bias))
+        if getattr(self, "_text_keep", None) is not None:
+            ws.y.mul_(self._text_keep)   # zero the padded tokens (they remain keys/values)
 
     def _embed_time(self):
         ws, te = self.ws, self.dit.t_embedder
@@ -441,6 +455,11 @@ class TTAEngine:
         if ex is not None and ex.hidden[b] is not None:
             x_out.add_(ex.hidden[b].to(BF16)[None, :])
         self._ws_holds = b
+        if getattr(self, "debug", None) is not None:
+            for nm in ("mod", "xm1", "qkv", "qk", "o", "x1", "xn", "qc", "qcn", "kvc", "kcn", "oc", "x2", "xm2", "h1", "h3", "h", "y"):
+                self._tap(b, "f_" + nm, getattr(ws, nm))
+            self._tap(b, "f_xin", x_in)
+            self._tap(b, "f_xout", x_out)
 
     # ------------------------------------------------------------------ block backward (dx in ws.dx, in place)
     def _block_bwd(self, b: int, x_in, ex: Optional[Extras]):
@@ -451,6 +470,8 @@ class TTAEngine:
         scale_msa, gate_msa = mod[:, C:2 * C], mod[:, 2 * C:3 * C]
         scale_mlp, gate_mlp = mod[:, 4 * C:5 * C], mod[:, 5 * C:6 * C]
         dx = ws.dx
+        tap = self._tap
+        tap(b, "dx_out", dx)
         want_mod = ex is not None and ex.need_dmod
         dmod = ws.dmod if want_mod else None
         if want_mod:
@@ -461,6 +482,7 @@ class TTAEngine:
         # ---- FFN
         ops.gate_mul(ws.g1, dx, gate_mlp, tokens_per_frame=tpf, branch=ws.branch_m if want_mod else None,
                      dgate_acc=dmod[:, 5 * C:6 * C] if want_mod else None)
+        tap(b, "ffn_gout", ws.g1)
         s1, s3, s2 = st["w1"], st["w3"], st["w2"]
         if s1.has_lora or s3.has_lora:
             self._linear_bwd(s2, ws.g1, ws.h, ops.epi(ops.EPI_STORE, ws.h), "w2")      # dh overwrites h (h no longer needed)
@@ -472,9 +494,11 @@ class TTAEngine:
             self._linear_bwd(s2, ws.g1, ws.h, ops.epi(ops.EPI_SWIGLU_BWD, ws.dh1, d2=ws.dh3, aux1=ws.h1, aux2=ws.h3), "w2")
             ops.gemm(N, C, [(ws.dh1, s1.W, self.F, True, None), (ws.dh3, s3.W, self.F, True, None)],
                      ops.epi(ops.EPI_STORE, ws.g2))
+        tap(b, "ffn_gin", ws.g2)
         ops.ln_mod_bwd(dx, ws.g2, ws.x2, scale_mlp, dx_resid=dx, tokens_per_frame=tpf,
                        dscale_acc=dmod[:, 4 * C:5 * C] if want_mod else None,
                        dshift_acc=dmod[:, 3 * C:4 * C] if want_mod else None)
+        tap(b, "dx_after_ffn", dx)
         # ---- cross attention
         if Nn > 0:
             dxn = dx[Nc:]
@@ -494,13 +518,16 @@ class TTAEngine:
             self._linear_bwd(st["kv_linear"], ws.dkvc, ws.y, None, "kv_linear")                    # adapter grads only
             s = st["q_linear"]
             self._linear_bwd(s, ws.dqc, ws.xn, ops.epi(ops.EPI_STORE, ws.g2[:Nn]), "q_linear")    # d xn
+            tap(b, "cross_gin", ws.g2[:Nn])
             nrm = blk.pre_crs_attn_norm
             ops.ln_mod_bwd(dxn, ws.g2[:Nn], ws.x1[Nc:], nrm.weight, dx_resid=dxn, tokens_per_frame=tpf, affine=True,
                            dscale_acc=self._ngrad(ex, b, "pre_crs_attn_norm.weight", nrm.weight) if ng else None,
                            dshift_acc=self._ngrad(ex, b, "pre_crs_attn_norm.bias", nrm.bias) if ng else None)
+        tap(b, "dx_after_cross", dx)
         # ---- self attention
         ops.gate_mul(ws.g1, dx, gate_msa, tokens_per_frame=tpf, branch=ws.branch_a if want_mod else None,
                      dgate_acc=dmod[:, 2 * C:3 * C] if want_mod else None)
+        tap(b, "attn_gout", ws.g1)
         s = st["proj"]
         self._linear_bwd(s, ws.g1, ws.o, ops.epi(ops.EPI_STORE, ws.g2), "proj")                   # dO
         q = ws.qk.view(N, 2 * H, D)[:, :H]
@@ -518,15 +545,23 @@ class TTAEngine:
                                 dwk_acc=self._ngrad(ex, b, "attn.k_norm.weight", blk.attn.k_norm.weight) if ng else None)
         s = st["qkv"]
         self._linear_bwd(s, ws.dqkv, ws.xm1, ops.epi(ops.EPI_STORE, ws.g1), "qkv")                # d xm1
+        tap(b, "attn_gin", ws.g1)
         ops.ln_mod_bwd(dx, ws.g1, x_in, scale_msa, dx_resid=dx, tokens_per_frame=tpf,
                        dscale_acc=dmod[:, C:2 * C] if want_mod else None,
                        dshift_acc=dmod[:, 0:C] if want_mod else None)
+        tap(b, "dx_in", dx)
         if want_mod:
             ex.d_mod[b] = dmod.clone()
             if ex.need_dt:
                 ada = blk.adaLN_modulation[1]
                 ops.skinny_linear_bwd(ws.dt, dmod, self._t_for_block(b, ex), ada.weight, act=1)
                 ex.d_t[b] = ws.dt.clone()
+
+    def _tap(self, b: int, name: str, t: torch.Tensor):
+        """debug hook: engine.debug = {} collects clones of backward intermediates (tests only)"""
+        dbg = getattr(self, "debug", None)
+        if dbg is not None:
+            dbg[(b, name)] = t.detach().float().clone()
 
     @staticmethod
     def _ngrad(ex: Extras, b: int, name: str, like: torch.Tensor):

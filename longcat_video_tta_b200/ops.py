@@ -45,6 +45,11 @@ def _call(name: str, *args):
     check(getattr(_lib.load(), name)(*args), name)
 
 
+def kernel_launches() -> int:
+    """CUDA kernels launched by libb200tta.so so far in this process."""
+    return int(_lib.load().b200tta_launch_count())
+
+
 def selfcheck():
     check(_lib.load().b200tta_selfcheck(), "b200tta_selfcheck")
 

@@ -23,7 +23,8 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/b200tta.h but not exported by libb200tta.so"
     from longcat_video_tta_b200._lib import SIGNATURES
-    assert set(SIGNATURES) | {"b200tta_last_error"} == set(names), set(names) ^ (set(SIGNATURES) | {"b200tta_last_error"})
+    extra = {"b200tta_last_error", "b200tta_launch_count"}
+    assert set(SIGNATURES) | extra == set(names), set(names) ^ (set(SIGNATURES) | extra)
 
 
 def test_struct_layouts_match_header(tmp_path):
