@@ -151,7 +151,7 @@ class B200DiT(nn.Module):
         cfg = make_config(name, **overrides)
         with torch.device("meta"):
             m = cls(cfg)
-        m = m.to_empty(device=device).to(BF16)
+        m = m.to(BF16).to_empty(device=device)
         g = torch.Generator(device=device).manual_seed(seed)
         with torch.no_grad():
             for n, p in m.named_parameters():

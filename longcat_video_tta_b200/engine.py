@@ -11,7 +11,8 @@ copies).  Per-block recompute mirrors the reference's ``torch.utils.checkpoint``
 
 What is saved where (HBM layout, N tokens, C hidden, F ffn):
   xs[L+1][N,C] bf16      block inputs (checkpoints) and the final hidden state
-  ws.*                   one block's intermediates: xm1, qkv, qk(normed+roped), o, lse, x1, xn, qc, qcn, kvc, kcn, oc,
+  o_all[L][N,C], lse_all[L][H,N]   self-attention output and log-sum-exp of every block (the recompute pass skips attention)
+  ws.*                   one block's intermediates: xm1, qkv, qk(normed+roped), x1, xn, qc, qcn, kvc, kcn, oc,
                          lsec, x2, xm2, h1, h3, h and the gradient temporaries; re-used by every block
   grad_flat f32          all adapter gradients back to back (LoRA "down" gradients transposed, see b200tta.h)
 """
@@ -282,8 +283,11 @@ class TTAEngine:
         ws.y1, ws.y = e(M, C), e(M, C)
         ws.mod, ws.modf = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32)
         ws.xm1, ws.xm2 = e(N, C), e(N, C)
-        ws.qkv, ws.qk, ws.o = e(N, 3 * C), e(N, 2 * C), e(N, C)
-        ws.lse, ws.delta = e(H, N, dt=F32), e(H, N, dt=F32)
+        ws.qkv, ws.qk = e(N, 3 * C), e(N, 2 * C)
+        # self-attention output + log-sum-exp are kept for EVERY block (312 MB per block at 37k tokens) so that the
+        # per-block recompute in the backward never re-runs the attention forward (the most expensive op to redo)
+        ws.o_all, ws.lse_all = e(self.L, N, C), e(self.L, H, N, dt=F32)
+        ws.delta = e(H, N, dt=F32)
         ws.x1, ws.x2 = e(N, C), e(N, C)
         ws.xn, ws.qc, ws.qcn, ws.oc = e(Nn, C), e(Nn, C), e(Nn, C), e(Nn, C)
         ws.kvc, ws.kcn = e(M, 2 * C), e(M, C)
@@ -393,8 +397,9 @@ class TTAEngine:
         return self.ws.t
 
     # ------------------------------------------------------------------ block forward
-    def _block_fwd(self, b: int, x_in, x_out, ex: Optional[Extras]):
+    def _block_fwd(self, b: int, x_in, x_out, ex: Optional[Extras], recompute: bool = False):
         ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
+        ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
         blk, st = self.dit.blocks[b], self.sites[b]
         N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
         ada = blk.adaLN_modulation[1]
@@ -418,7 +423,8 @@ class TTAEngine:
         q = ws.qk.view(N, 2 * H, D)[:, :H]
         k = ws.qk.view(N, 2 * H, D)[:, H:]
         v = ws.qkv.view(N, 3 * H, D)[:, 2 * H:]
-        ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
+        if not recompute:
+            ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
         s = st["proj"]
         self._linear_fwd_xa(s, ws.o, ops.epi(ops.EPI_GATE_RESID, ws.x1, bias=s.bias, resid=x_in, gate=gate_msa,
                                              tokens_per_frame=tpf, d2=ws.branch_a if keep_branch else None), "proj")
@@ -464,6 +470,7 @@ class TTAEngine:
     # ------------------------------------------------------------------ block backward (dx in ws.dx, in place)
     def _block_bwd(self, b: int, x_in, ex: Optional[Extras]):
         ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
+        ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
         blk, st = self.dit.blocks[b], self.sites[b]
         N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
         mod = ws.mod
@@ -631,7 +638,7 @@ class TTAEngine:
             ex.d_hidden_final = ws.dx.float().sum(0)
         for b in reversed(range(self.L)):
             if getattr(self, "_ws_holds", None) != b:  # the last block's intermediates are still in the workspace
-                self._block_fwd(b, ws.xs[b], ws.g2, ex)   # recompute (block output discarded into g2)
+                self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
             self._block_bwd(b, ws.xs[b], ex)
         self._ws_holds = None
 
