@@ -620,6 +620,9 @@ class TTAEngine:
             if only_out_bias:
                 return
         self.grad_flat.zero_()
+        if ex is not None:
+            for v in ex.d_norm.values():
+                v.zero_()
         # final layer: d xf = dpred W_lin ; context rows are zero
         ws.g1[: geo.Nc].zero_()
         ops.gemm(geo.Nn, C, [(ws.dpred, fl.linear.weight, 64, True, None)], ops.epi(ops.EPI_STORE, ws.g1[geo.Nc:]))
@@ -663,26 +666,28 @@ def _geometry_for(dit, hidden_states, n_cond, M) -> Geometry:
 
 
 class _DiTFunction(torch.autograd.Function):
-    """pred = dit(hidden, timestep, text) with gradients for the adapter parameters only."""
+    """pred = dit(hidden, timestep, text) with gradients for the adapter parameters only (LoRA tensors and, when an
+    ``adapters`` wrapper is given, its delta / norm / FiLM trainables)."""
 
     @staticmethod
-    def forward(ctx, dit, hidden_states, timestep, text_valid, n_cond, *params):
+    def forward(ctx, dit, adapter, hidden_states, timestep, text_valid, n_cond, n_lora, *params):
         eng = dit.engine
         geo = _geometry_for(dit, hidden_states, n_cond, text_valid.shape[0])
-        eng._prepare(geo, None)
+        ex = adapter.build_extras() if adapter is not None else None
+        eng._prepare(geo, ex)
         ws = eng.ws
         ops.noise_patchify(ws.P, None, None, hidden_states[0].to(BF16).contiguous(), None, None, None)
         ws.timestep.copy_(timestep.reshape(-1).to(BF16).float())  # the DiT re-casts the timestep to its dtype first
-        eng.forward_tokens(text_valid)
+        eng.forward_tokens(text_valid, ex)
         out = torch.empty(1, 16, geo.T, geo.Hl, geo.Wl, dtype=F32, device=eng.device)
         ops.unpatchify(out[0], ws.pred, geo.T, geo.Hl, geo.Wl)
-        ctx.dit, ctx.geo, ctx.text_valid = dit, geo, text_valid
-        ctx.n_params = len(params)
+        ctx.dit, ctx.geo, ctx.adapter, ctx.ex = dit, geo, adapter, ex
+        ctx.n_lora, ctx.n_params = n_lora, len(params)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        eng, geo = ctx.dit.engine, ctx.geo
+        eng, geo, ex = ctx.dit.engine, ctx.geo, ctx.ex
         if eng.geo != geo:
             raise RuntimeError("the engine workspace was re-planned between forward and backward")
         ws = eng.ws
@@ -691,16 +696,21 @@ class _DiTFunction(torch.autograd.Function):
         if geo.n_cond > 0 and bool((g[:, : geo.n_cond] != 0).any()):
             raise NotImplementedError("gradient flowing into context-frame predictions is not supported")
         ops.latent_to_tokens(ws.dpred, g, geo.T, geo.Hl, geo.Wl, geo.n_cond)
-        eng.backward_tokens(None)
+        eng.backward_tokens(ex)
         grads = []
         for s in eng.lora_sites():
             for p, gr in zip(s.params, s.param_grads()):
                 grads.append(gr.to(p.dtype).contiguous() if p.requires_grad else None)
+        assert len(grads) == ctx.n_lora
+        if ctx.adapter is not None:
+            for p, gr in zip(ctx.adapter.trainable(), ctx.adapter.grads_from(ex)):
+                grads.append(gr.reshape(p.shape).to(p.dtype))
         assert len(grads) == ctx.n_params
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)
 
 
-def dit_forward_autograd(dit, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask, num_cond_latents):
+def dit_forward_autograd(dit, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask, num_cond_latents,
+                         adapter=None):
     if not hidden_states.is_cuda:
         from ._lib import B200TTAError
         raise B200TTAError("B200DiT runs on a B200 only: inputs are on %s and there is no CPU fallback" % hidden_states.device)
@@ -708,11 +718,13 @@ def dit_forward_autograd(dit, hidden_states, timestep, encoder_hidden_states, en
     text_valid = eng.pack_text(encoder_hidden_states, encoder_attention_mask)
     if timestep.dim() == 1:
         timestep = timestep.unsqueeze(1).expand(-1, hidden_states.shape[2])
-    params = eng.adapter_parameters()
+    lora_params = eng.adapter_parameters()
+    params = lora_params + (list(adapter.trainable()) if adapter is not None else [])
     if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        return _DiTFunction.apply(dit, hidden_states, timestep, text_valid, num_cond_latents, *params)
+        return _DiTFunction.apply(dit, adapter, hidden_states, timestep, text_valid, num_cond_latents, len(lora_params), *params)
     with torch.no_grad():
-        return _DiTFunction.forward(_NoCtx(), dit, hidden_states, timestep, text_valid, num_cond_latents, *params)
+        return _DiTFunction.forward(_NoCtx(), dit, adapter, hidden_states, timestep, text_valid, num_cond_latents,
+                                    len(lora_params), *params)
 
 
 class _NoCtx:

@@ -36,23 +36,24 @@ def _state_like(p: torch.Tensor, fp32: bool):
 class TTAStepper:
     def __init__(self, dit, *, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, per_tensor_clip: bool = False, master_weights: bool = True,
-                 faithful_bf16: bool = False, extra_params: Optional[Sequence[torch.nn.Parameter]] = None,
-                 extras: Optional[Extras] = None, extra_grad_fn=None, train_lora: bool = True, process_group=None):
+                 faithful_bf16: bool = False, adapter=None, train_lora: bool = True, build_optimizer: bool = True,
+                 process_group=None):
         """
         master_weights : keep an fp32 master copy (and fp32 Adam moments) of every bf16 adapter tensor.  The
                          reference keeps params and moments in bf16 (run_lora_tta.py:332) where updates below half an
                          ulp are lost; ``faithful_bf16=True, master_weights=False`` reproduces
                          that op-by-op rounding instead.
-        extra_params   : non-LoRA trainables (delta vectors, FiLM corrections, norm weights ...); ``extra_grad_fn(ex)``
-                         returns their fp32 gradients (same order) after the backward.
+        adapter        : one of adapters.{DeltaA,DeltaB,DeltaC,NormTuneForward,FiLMAdapter}Wrapper: supplies the non-LoRA
+                         trainables (``trainable()``), where they enter the network (``build_extras()``) and their
+                         fp32 gradients after the backward (``grads_from(extras)``).
         """
         self.dit = dit
         self.eng: TTAEngine = dit.engine
         self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
         self.faithful = faithful_bf16
-        self.extras = extras
-        self.extra_grad_fn = extra_grad_fn
-        self.extra_params = list(extra_params or [])
+        self.adapter = adapter
+        self.extras = None
+        self.extra_params = list(adapter.trainable()) if adapter is not None else []
         self.pg = process_group
         self.world = 1
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
@@ -88,6 +89,8 @@ class TTAStepper:
             if use_master:
                 e["master"] = p.data.float()
             self._extra_entries.append(e)
+        if not build_optimizer:
+            entries, self._extra_entries = [], []
         self.group = ParamGroup(entries + self._extra_entries, dev, per_tensor_clip)
         self.n_params = sum(e["param"].numel() for e in self.group.entries)
 
@@ -103,7 +106,7 @@ class TTAStepper:
         eng = self.eng
         text_valid = eng.pack_text(prompt_embeds, prompt_mask)
         geo = self._geometry(cond, target, text_valid)
-        ex = self.extras
+        ex = self.extras = self.adapter.build_extras() if self.adapter is not None else None
         eng._prepare(geo, ex)
         eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
         eng.forward_tokens(text_valid, ex)
@@ -128,8 +131,8 @@ class TTAStepper:
 
     def optimizer_step(self, lr: float):
         self.step_count += 1
-        if self.extra_grad_fn is not None and self._extra_entries:
-            for e, g in zip(self._extra_entries, self.extra_grad_fn(self.extras)):
+        if self.adapter is not None and self._extra_entries:
+            for e, g in zip(self._extra_entries, self.adapter.grads_from(self.extras)):
                 e["grad"].copy_(g.reshape(e["grad"].shape))
         self._sync_grads()
         for s, ents in self._staged:
@@ -154,9 +157,10 @@ class TTAStepper:
         eng = self.eng
         text_valid = eng.pack_text(prompt_embeds, prompt_mask)
         geo = self._geometry(cond, target, text_valid)
-        eng._prepare(geo, self.extras)
-        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
-        eng.forward_tokens(text_valid, self.extras)
+        ex = self.adapter.build_extras() if self.adapter is not None else None
+        eng._prepare(geo, ex)
+        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.reshape(-1)[:1].to(F32))
+        eng.forward_tokens(text_valid, ex)
         eng._ws_holds = None
         return eng.loss_and_dpred(False).clone()
 
