@@ -125,9 +125,9 @@ class TTAStepper:
 
     def _sync_grads(self):
         if self.world > 1:
-            bufs = [self.eng.grad_flat] + [e["grad"] for e in self._extra_entries]
-            for b in bufs:
-                torch.distributed.all_reduce(b, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            from .dist import all_reduce_grads
+            bufs = ([self.eng.grad_flat] if self._n_lora_entries else []) + [e["grad"] for e in self._extra_entries]
+            all_reduce_grads(bufs, self.pg)
 
     def optimizer_step(self, lr: float):
         self.step_count += 1

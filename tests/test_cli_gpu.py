@@ -1,0 +1,51 @@
+"""GPU: the drop-in scripts run end to end on synthetic latents (tiny DiT) and write the reference's output files."""
+import json
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def test_run_lora_tta_script_outputs(tmp_path):
+    _need_gpu()
+    from longcat_video_tta_b200 import cli
+    out = tmp_path / "lora"
+    summary = cli.run("lora", f"--output-dir {out} --synthetic --model tiny --latent-hw 32,32 --tta-total-frames 17 "
+                              "--tta-context-frames 5 --lora-rank 16 --lora-alpha 32 --num-steps 3 --max-videos 2 "
+                              "--es-check-every 1 --save-lora-weights --skip-generation".split())
+    assert summary["num_success"] == 2
+    cfg = json.loads((out / "config.json").read_text())
+    assert cfg["lora"]["rank"] == 16 and cfg["lora"]["num_modules"] == 10 and cfg["lora"]["trainable_params"] == 212992
+    ck = json.loads((out / "checkpoint.json").read_text())
+    assert ck["next_idx"] == 2 and len(ck["results"]) == 2
+    r = ck["results"][0]
+    for key in ("idx", "video_name", "train_time", "es_check_time", "final_loss", "num_train_steps", "early_stopping_info",
+                "success", "total_time"):
+        assert key in r
+    assert r["early_stopping_info"]["total_checks"] >= 2          # val frames exist (5 latent frames: 2 / 2 / 1)
+    w = torch.load(out / "lora_weights" / "synthetic_0000_lora.pt")
+    assert set(w) == {f"lora_{i}.{k}" for i in range(10) for k in ("down", "up")}
+    assert w["lora_0.down"].shape == (16, 512) and w["lora_0.up"].shape == (1536, 16)
+    # resume: nothing left to do
+    again = cli.run("lora", f"--output-dir {out} --synthetic --model tiny --latent-hw 32,32 --max-videos 2".split())
+    assert again["num_videos"] == 2
+
+
+@pytest.mark.parametrize("method,flags", [
+    ("delta_a", "--delta-steps 2"), ("delta_b", "--delta-steps 2 --num-groups 2"), ("delta_c", "--delta-steps 2"),
+    ("norm_tune", "--norm-steps 2 --norm-target all_norm"), ("film", "--film-steps 2 --num-groups 2 --film-mode shift_scale"),
+])
+def test_adapter_scripts_run(tmp_path, method, flags):
+    _need_gpu()
+    from longcat_video_tta_b200 import cli
+    out = tmp_path / method
+    s = cli.run(method, (f"--output-dir {out} --synthetic --model tiny --latent-hw 32,32 --tta-total-frames 17 "
+                         f"--tta-context-frames 5 --max-videos 1 --es-disable {flags}").split())
+    assert s["num_success"] == 1, s["results"]
+    assert s["results"][0]["num_train_steps"] == 2 and s["results"][0]["final_loss"] > 0

