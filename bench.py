@@ -24,6 +24,7 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC, UNIT = "tta_steps_per_sec", "steps/s"
+_OUT = sys.stdout
 WORKLOAD = ("LongCat-Video 13.6B LoRA r=16 (qkv,proj; 48 blocks) TTA step, bf16, synthetic 480p 93-frame latent "
             "[16,24,60,104] = 4 context + 20 noised latent frames (37440 tokens), 512 text tokens")
 
@@ -147,7 +148,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -234,6 +235,9 @@ def run_b200(args):
     prof = {}
     if rank == 0:
         prof = profile_step(ops, lambda: one_step(cond, train, prompt, mask, 0))
+    else:
+        one_step(cond, train, prompt, mask, 0)   # every rank takes part in the step's all-reduce
+        torch.cuda.synchronize()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -289,7 +293,7 @@ def run_b200(args):
                                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
         "loss_first_last": [loss_vals[0], loss_vals[-1]],
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -354,7 +358,18 @@ def profile_step(ops, fn):
     return out
 
 
+def _protect_stdout():
+    """stdout must carry exactly ONE JSON line: route everything else (NCCL banners, library prints) to stderr and
+    return a file object bound to the real stdout."""
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main():
+    global _OUT
+    _OUT = _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
