@@ -48,6 +48,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(job):
         src, obj = job
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if os.environ.get("B200TTA_ATTN_DEBUG"):  # developer timing counters in the attention kernels (scratch/bench_attn.py)
+            cmd.insert(1, "-DB200TTA_ATTN_DEBUG=1")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)

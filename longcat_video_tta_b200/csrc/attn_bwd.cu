@@ -1,29 +1,62 @@
 // Flash-style attention backward for sm_100a, head_dim 128, bf16 -- recomputes S = Q K^T from Q, K and the saved
-// log-sum-exp (no S/P tensors are ever stored).  Three kernels, all deterministic (no atomics):
+// log-sum-exp (no S/P tensors are ever stored).  Three kernels, no atomics:
 //   delta_kernel : delta[h, i] = sum_d dO[i,h,d] * O[i,h,d]
-//   dq_kernel    : one CTA per (128-row query tile, head), loop over K/V blocks:
-//                    S = Q K^T, dP = dO V^T (SS) -> dS = P o (dP - delta) (bf16 over dP in TMEM) -> dQ += dS K (TS)
-//   dkv_kernel   : one CTA per (128-row K/V block, head), loop over the query tiles that see it:
-//                    S^T = K Q^T, dP^T = V dO^T (SS) -> P^T, dS^T (bf16 in TMEM) -> dV += P^T dO, dK += dS^T Q (TS)
+//   dq_kernel    : one CTA per (128-row query tile, head); Q and dO live in TENSOR MEMORY as bf16 A operands; K/V stream
+//                  through shared memory in 64-row sub-blocks:
+//                    S = Q K^T, dP = dO V^T (TS, N=64) -> dS = P o (dP - delta) (bf16 over dP in TMEM) -> dQ += dS K (TS)
+//   dkv_kernel   : one CTA per (128-row K/V block, head); K, V resident in shared memory; Q/dO stream through in 64-row
+//                  sub-tiles together with their LSE / delta values (staged by the producer warp):
+//                    S^T = K Q^T, dP^T = V dO^T (SS, N=64) -> P^T, dS^T (bf16 in TMEM) -> dV += P^T dO, dK += dS^T Q (TS)
+// Why the A operands sit in TMEM where they fit: an SS-form tcgen05.mma re-reads its 128 x 16 A slice (4 KB) and its
+// N x 16 B slice from shared memory for every instruction, and shared memory delivers 128 B/clk -- measured
+// (scratch/mma_rate.cu): SS N=64 costs 48 clk, N=32 40 clk, while the TS form (A in TMEM) runs at the tensor rate N/2.
+// Pipelining: the S/dP accumulators are double-buffered in TMEM (2 x 128 columns) and two compute warpgroups alternate
+// sub-tiles, so the exponentials of sub-tile u overlap the tensor-core work of sub-tiles u-1 / u+1.
+// The bf16 P / dS tiles overwrite the fp32 S / dP columns they were computed from; each thread's stores land inside
+// the column range it loaded itself ([32h, 32h+16) of [32h, 32h+32)), so no cross-thread barrier is needed.
 // The same shared-memory tile serves as a K-major operand (contraction over d) and as an MN-major operand
 // (contraction over tokens) -- only the UMMA descriptor differs, nothing is transposed in memory.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 one thread per TMEM lane (row).
+// Warp roles: warp 0 TMA producer; warps 1 and 2 MMA issuers, one per S/dP buffer (= per compute group): any
+// shared-memory access of an issuing thread (an mbarrier poll included) queues behind its own outstanding
+// tcgen05.mma and costs ~100 clk during which a single issuer leaves the tensor pipe idle (measured,
+// scratch/mma_issue.cu: 1025 clk per sub-block with one issuer and three waits, 768 = pipe time with two issuers
+// alternating).  Each issuer runs warp-converged with one elected lane issuing -- a divergent `if (lane == 0)` region
+// costs ~100 clk per MMA in uniform-register waterfall loops.  Warps 3-10 compute group 0, warps 11-18 compute group 1
+// (two threads per TMEM lane = row, 32 columns each).  The dQ / dK / dV accumulators are zeroed up front and every MMA
+// accumulates, so the two issuers need no ordering between each other; the fp32 summation order of the sub-block
+// contributions is therefore not fixed run to run (differences at rounding level).
 #include "host_common.h"
 #include "ptx.cuh"
+#include <stdlib.h>
+
+#ifndef B200TTA_ATTN_DEBUG
+#define B200TTA_ATTN_DEBUG 0
+#endif
 
 namespace b200 {
 namespace {
 
-constexpr int D = 128, BT = 128;
-constexpr int TILE_BYTES = 128 * 128 * 2, SUB_BYTES = TILE_BYTES / 2;
-constexpr int STAGES = 2;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = (2 + 2 * STAGES) * TILE_BYTES + 1024 + 256 + 2 * 2 * BT * 4;
+constexpr int D = 128, BT = 128, SUB = 64;
+constexpr int TILE_BYTES = BT * D * 2;        // resident [128 x 128] operand: two [128 x 64] swizzled halves
+constexpr int HALF_BYTES = TILE_BYTES / 2;
+constexpr int SUBT_BYTES = SUB * D * 2;       // streamed [64 x 128] operand: two [64 x 64] swizzled halves
+constexpr int SUBH_BYTES = SUBT_BYTES / 2;
+constexpr int DQ_STAGES = 6;                  // dq: only K/V sub-blocks live in shared memory
+constexpr int DKV_STAGES = 4;                 // dkv: K, V resident (64 KB) + Q/dO sub-tiles
+constexpr int GROUP_THREADS = 256;            // per TMEM buffer: two threads per row, 32 columns each
+constexpr int NUM_THREADS = 96 + 2 * GROUP_THREADS;   // producer warp, two MMA issuer warps, two compute groups
+constexpr int DS_BYTES = BT * SUB * 2;           // dS tile [128 x 64] bf16, K-major SW128
+constexpr int DQ_SMEM_BYTES = 2 * DQ_STAGES * SUBT_BYTES + 2 * DS_BYTES + 1024 + 512;
+static_assert(DQ_SMEM_BYTES <= 232448, "dq_kernel shared memory");
+constexpr int DKV_SMEM_BYTES = 2 * TILE_BYTES + 2 * DKV_STAGES * SUBT_BYTES + 1024 + 512 + DKV_STAGES * 2 * SUB * 4;
 constexpr int MAX_SEGS = 4;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct BwdParams {
-    CUtensorMap tma_q, tma_k, tma_v, tma_do;
+    CUtensorMap tma_k128, tma_v128;                        // box {64, 128}
+    CUtensorMap tma_q64, tma_do64, tma_k64, tma_v64;       // box {64, 64}
+    const __nv_bfloat16 *Q, *dO;
+    long long ldq, lddo;
     __nv_bfloat16 *dQ, *dK, *dV;
     long long lddq, lddk, lddv;
     const float* LSE;
@@ -31,8 +64,20 @@ struct BwdParams {
     int n_q, n_kv, heads;
     float scale, scale_log2;
     int n_seg;
+    int dbg_flags;   // debug builds only: 1 = dq producer re-uses stale smem, 2 = dq compute warps skip TMEM traffic and math
     int seg_q_begin[MAX_SEGS], seg_q_end[MAX_SEGS], seg_kv_len[MAX_SEGS], seg_item0[MAX_SEGS + 1];
 };
+
+#if B200TTA_ATTN_DEBUG
+__device__ long long g_dbg[32];
+#define DBG_ON (blockIdx.x == 0 && blockIdx.y == 0)
+#define DBG_CLK() clock64()
+#define DBG_SET(i, v) do { g_dbg[i] = (v); } while (0)
+#else
+#define DBG_ON false
+#define DBG_CLK() 0ll
+#define DBG_SET(i, v) do { } while (0)
+#endif
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -40,9 +85,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, uint32_t tmem_addr, float mul, bool do_store) {
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, uint32_t tmem_addr, float mul, bool do_store,
+                                               int c_begin, int c_end) {
 #pragma unroll 1
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(tmem_addr + c * 32, r);
         tmem_ld_wait();
@@ -58,6 +104,44 @@ __device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, uint32_t tmem
             }
         }
     }
+}
+
+// S-like MMA, SS form: D[128 x 64] = A[128 x 128(d)] (resident in smem, K-major) * B[64 x 128(d)]^T (streamed, K-major)
+__device__ __forceinline__ void mma_ss_n64(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
+    constexpr uint32_t idesc = umma_idesc_bf16(BT, SUB, 0, 0);
+    const uint64_t ad = umma_desc_kmajor(a_smem), bd = umma_desc_kmajor(b_smem);
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            umma_ss_e(d_tmem, umma_desc_advance(ad, c * HALF_BYTES + ks * 32), umma_desc_advance(bd, c * SUBH_BYTES + ks * 32),
+                      idesc, (c | ks) ? 1u : 0u);
+}
+// S-like MMA, TS form: D[128 x 64] = A[128 x 128(d)] (bf16 in TMEM, 64 columns) * B[64 x 128(d)]^T (streamed, K-major)
+__device__ __forceinline__ void mma_ts_n64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem) {
+    constexpr uint32_t idesc = umma_idesc_bf16(BT, SUB, 0, 0);
+    const uint64_t bd = umma_desc_kmajor(b_smem);
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks)
+        umma_ts_e(d_tmem, a_tmem + ks * 8, umma_desc_advance(bd, (ks >> 2) * SUBH_BYTES + (ks & 3) * 32), idesc, ks ? 1u : 0u);
+}
+// accumulate MMA: D[128 x 128(d)] += A[128 x 64] (bf16 in TMEM) * B[64 x 128(d)] (streamed tile read MN-major).
+// A's 64 contraction columns sit where the compute threads left them: 16-column runs at +0 and +32.
+__device__ __forceinline__ void mma_ts_k64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem) {
+    constexpr uint32_t idesc = umma_idesc_bf16(BT, D, 0, 1);
+    const uint64_t bd = umma_desc_mnmajor(b_smem, SUBH_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < SUB / 16; ++ks)
+        umma_ts_e(d_tmem, a_tmem + (ks >> 1) * 32 + (ks & 1) * 8, umma_desc_advance(bd, ks * 2048), idesc, 1u);
+}
+
+// accumulate MMA, SS form: D[128 x 128(d)] += A[128 x 64] (bf16 tile in smem, K-major SW128) * B[64 x 128(d)] (MN-major)
+__device__ __forceinline__ void mma_ss_k64(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
+    constexpr uint32_t idesc = umma_idesc_bf16(BT, D, 0, 1);
+    const uint64_t ad = umma_desc_kmajor(a_smem), bd = umma_desc_mnmajor(b_smem, SUBH_BYTES);
+#pragma unroll
+    for (int ks = 0; ks < SUB / 16; ++ks)
+        umma_ss_e(d_tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 2048), idesc, 1u);
 }
 
 // ------------------------------------------------------------------------------------ delta = rowsum(dO * O)
@@ -78,22 +162,30 @@ __global__ void __launch_bounds__(256) delta_kernel(float* __restrict__ delta, c
 }
 
 // ------------------------------------------------------------------------------------ dQ
+// TMEM: buffer b in {0,1}: S at [128 b, 128 b + 64), dP at [128 b + 64, 128 b + 128); dQ at [256, 384);
+//       Q (bf16, 64 columns) at [384, 448); dO (bf16) at [448, 512).
+// dS leaves the compute threads through a double-buffered shared-memory tile (K-major SW128, the A operand of the
+// dQ MMA), NOT through TMEM: the S/dP buffer is then free as soon as the compute group has LOADED it, so S/dP(u+2)
+// can be issued ~1000 clk earlier than with dS aliased over dP -- the dependency cycle
+// "S/dP -> exp/ds -> dQ MMA -> next S/dP" was what kept the tensor pipe at ~60 %.
 __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constant__ BwdParams p) {
+    constexpr int STAGES = DQ_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_s = smem;
-    uint8_t* do_s = q_s + TILE_BYTES;
-    uint8_t* k_s = do_s + TILE_BYTES;              // [STAGES]
-    uint8_t* v_s = k_s + STAGES * TILE_BYTES;      // [STAGES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + STAGES * TILE_BYTES);
+    uint8_t* k_s = smem;                           // [STAGES][SUBT_BYTES]
+    uint8_t* v_s = k_s + STAGES * SUBT_BYTES;      // [STAGES][SUBT_BYTES]
+    uint8_t* ds_s = v_s + STAGES * SUBT_BYTES;     // [2][128 rows x 128 B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ds_s + 2 * DS_BYTES);
     uint64_t* qdo_full = bars;
     uint64_t* k_full = bars + 1;
     uint64_t* k_empty = k_full + STAGES;
     uint64_t* v_full = k_empty + STAGES;
     uint64_t* v_empty = v_full + STAGES;
-    uint64_t* sdp_full = v_empty + STAGES;
-    uint64_t* ds_full = sdp_full + 1;
-    uint64_t* dq_done = ds_full + 1;
+    uint64_t* sdp_full = v_empty + STAGES;   // [2] tcgen05.commit: S and dP of the buffer are complete
+    uint64_t* sdp_free = sdp_full + 2;       // [2] compute group: both tiles are in registers
+    uint64_t* ds_full = sdp_free + 2;        // [2] compute group: dS tile written (and fenced to the async proxy)
+    uint64_t* ds_free = ds_full + 2;         // [2] tcgen05.commit: the dQ MMA has consumed the dS tile
+    uint64_t* dq_done = ds_free + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dq_done + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,118 +195,178 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
     const int q0 = p.seg_q_begin[seg] + (item - p.seg_item0[seg]) * BT;
     const int q_end = p.seg_q_end[seg];
     const int kv_len = p.seg_kv_len[seg];
-    const int n_blocks = (kv_len + BT - 1) / BT;
+    const int n_sub = (kv_len + SUB - 1) / SUB;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tma_q); tma_prefetch_desc(&p.tma_k); tma_prefetch_desc(&p.tma_v); tma_prefetch_desc(&p.tma_do);
-        mbar_init(qdo_full, 1);
+        tma_prefetch_desc(&p.tma_k64); tma_prefetch_desc(&p.tma_v64);
+        mbar_init(qdo_full, 2 * GROUP_THREADS);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
-        mbar_init(sdp_full, 1); mbar_init(ds_full, BT); mbar_init(dq_done, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&sdp_full[b], 1); mbar_init(&sdp_free[b], GROUP_THREADS);
+            mbar_init(&ds_full[b], GROUP_THREADS); mbar_init(&ds_free[b], 1);
+        }
+        mbar_init(dq_done, 2);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dq = tmem_base + 256;
+    if (*tmem_ptr != 0) __trap();   // all 512 columns, one CTA per SM: the allocation starts at 0
+    constexpr uint32_t tmem_base = 0;
+    constexpr uint32_t t_dq = tmem_base + 256, t_q = tmem_base + 384, t_do = tmem_base + 448;
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(qdo_full, 2 * TILE_BYTES);
-            for (int c = 0; c < 2; ++c) {
-                tma_load_2d(q_s + c * SUB_BYTES, &p.tma_q, qdo_full, head * D + c * 64, q0);
-                tma_load_2d(do_s + c * SUB_BYTES, &p.tma_do, qdo_full, head * D + c * 64, q0);
-            }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_blocks; ++j) {
-                mbar_wait(&k_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&k_full[stage], TILE_BYTES);
+            for (int u = 0; u < n_sub; ++u) {
+                const int st = u % STAGES;
+                const uint32_t ph = (u / STAGES) & 1;
+                if (B200TTA_ATTN_DEBUG && (p.dbg_flags & 1) && u >= STAGES) {
+                    mbar_wait(&k_empty[st], ph ^ 1u); mbar_arrive(&k_full[st]);
+                    mbar_wait(&v_empty[st], ph ^ 1u); mbar_arrive(&v_full[st]);
+                    continue;
+                }
+                mbar_wait(&k_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&k_full[st], SUBT_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(k_s + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_k, &k_full[stage], head * D + c * 64, j * BT);
-                mbar_wait(&v_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&v_full[stage], TILE_BYTES);
+                    tma_load_2d(k_s + st * SUBT_BYTES + c * SUBH_BYTES, &p.tma_k64, &k_full[st], head * D + c * 64, u * SUB);
+                mbar_wait(&v_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&v_full[st], SUBT_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(v_s + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_v, &v_full[stage], head * D + c * 64, j * BT);
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    tma_load_2d(v_s + st * SUBT_BYTES + c * SUBH_BYTES, &p.tma_v64, &v_full[st], head * D + c * 64, u * SUB);
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(BT, BT, 0, 0);
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(BT, D, 0, 1);
-            mbar_wait(qdo_full, 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int j = 0; j < n_blocks; ++j) {
-                const uint32_t qa = smem_u32(q_s), da = smem_u32(do_s);
-                const uint32_t ka = smem_u32(k_s + stage * TILE_BYTES), va = smem_u32(v_s + stage * TILE_BYTES);
-                mbar_wait(&k_full[stage], phase);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(t_s, umma_desc_kmajor(qa + c * SUB_BYTES + ks * 32),
-                                umma_desc_kmajor(ka + c * SUB_BYTES + ks * 32), idesc_kk, (c | ks) ? 1u : 0u);
-                mbar_wait(&v_full[stage], phase);
-                tc_fence_after();
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(t_dp, umma_desc_kmajor(da + c * SUB_BYTES + ks * 32),
-                                umma_desc_kmajor(va + c * SUB_BYTES + ks * 32), idesc_kk, (c | ks) ? 1u : 0u);
-                umma_commit(sdp_full);
-                umma_commit(&v_empty[stage]);
-                mbar_wait(ds_full, j & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < BT / 16; ++ks)
-                    umma_ts(t_dq, t_dp + ks * 8, umma_desc_mnmajor(ka + ks * 2048, SUB_BYTES), idesc_mn, (j | ks) ? 1u : 0u);
-                umma_commit(&k_empty[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-            umma_commit(dq_done);
+    } else if (warp <= 2) {
+        // issuer w owns buffer w and the sub-blocks u = w, w+2, ...; whole warp converged, the elected lane issues.
+        // While one issuer polls its barriers the other one's MMAs keep the pipe busy.
+        const int w = warp - 1;
+        const uint32_t t_s = tmem_base + w * 128, t_dp = t_s + 64;
+        const uint32_t ds_a = smem_u32(ds_s + w * DS_BYTES);
+        mbar_wait(qdo_full, 0);
+        tc_fence_after();
+        long long w_kv = 0, w_ds = 0, w_free = 0, w_tot0 = DBG_CLK();
+        auto issue_sdp = [&](int u) {
+            const int st = u % STAGES;
+            const uint32_t ph = (u / STAGES) & 1;
+            long long c0 = DBG_CLK();
+            mbar_wait2(&k_full[st], ph, &v_full[st], ph);
+            long long c1 = DBG_CLK(); w_kv += c1 - c0;
+            if (u >= 2) mbar_wait(&sdp_free[w], ((u >> 1) - 1) & 1);   // the group has loaded S/dP(u - 2)
+            w_free += DBG_CLK() - c1;
+            tc_fence_after();
+            mma_ts_n64(t_s, t_q, smem_u32(k_s + st * SUBT_BYTES));
+            mma_ts_n64(t_dp, t_do, smem_u32(v_s + st * SUBT_BYTES));
+            umma_commit_e(&sdp_full[w]);
+            umma_commit_e(&v_empty[st]);
+        };
+        if (w < n_sub) issue_sdp(w);
+        for (int u = w; u < n_sub; u += 2) {
+            const int st = u % STAGES;
+            if (u + 2 < n_sub) issue_sdp(u + 2);
+            long long c0 = DBG_CLK();
+            mbar_wait(&ds_full[w], (u >> 1) & 1);
+            w_ds += DBG_CLK() - c0;
+            tc_fence_after();
+            mma_ss_k64(t_dq, ds_a, smem_u32(k_s + st * SUBT_BYTES));
+            umma_commit_e(&k_empty[st]);
+            umma_commit_e(&ds_free[w]);
+        }
+        umma_commit_e(dq_done);
+        if (DBG_ON && warp == 1 && lane == 0) {
+            DBG_SET(0, DBG_CLK() - w_tot0); DBG_SET(1, w_ds); DBG_SET(2, (n_sub + 1) / 2); DBG_SET(3, w_kv); DBG_SET(10, w_free);
         }
     } else {
+        const int g = (warp - 3) >> 3;               // compute group: handles sub-blocks u = g, g+2, ...
+        const int half = ((warp - 3) >> 2) & 1;      // columns [32 half, 32 half + 32) of the 64-wide sub-block
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const int q_row = q0 + row;
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
         const bool row_ok = q_row < q_end;
-        const float lse2 = row_ok ? p.LSE[(long long)head * p.n_q + q_row] * LOG2E : 0.f;
-        const float dlt = row_ok ? p.delta[(long long)head * p.n_q + q_row] : 0.f;
-        for (int j = 0; j < n_blocks; ++j) {
-            mbar_wait(sdp_full, j & 1);
-            tc_fence_after();
-            const int valid = kv_len - j * BT;
-#pragma unroll 1
-            for (int c = 0; c < BT / 32; ++c) {
-                uint32_t s[32], dp[32], pk[16];
-                tmem_ld_32x32b_x32(t_s + lane_addr + c * 32, s);
-                tmem_ld_32x32b_x32(t_dp + lane_addr + c * 32, dp);
-                tmem_ld_wait();
+        const int oc = g * 2 + half;                 // this thread's quarter of the row for the one-off row work
+        {   // Q and dO rows -> TMEM as packed bf16 pairs (word w of a row = elements 2w, 2w+1 = one TMEM column)
+            uint32_t qw[16], dw[16];
+            const uint4* qsrc = reinterpret_cast<const uint4*>(p.Q + (long long)q_row * p.ldq + head * D + oc * 32);
+            const uint4* dsrc = reinterpret_cast<const uint4*>(p.dO + (long long)q_row * p.lddo + head * D + oc * 32);
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(s[i]), p.scale_log2, -lse2));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(s[i + 1]), p.scale_log2, -lse2));
-                    if (!row_ok || c * 32 + i >= valid) p0 = 0.f;
-                    if (!row_ok || c * 32 + i + 1 >= valid) p1 = 0.f;
-                    pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - dlt), p1 * (__uint_as_float(dp[i + 1]) - dlt));
-                }
-                tmem_st_32x32b_x16(t_dp + lane_addr + c * 16, pk);
+            for (int i = 0; i < 4; ++i) {
+                const uint4 a = row_ok ? __ldg(qsrc + i) : make_uint4(0, 0, 0, 0);
+                const uint4 b = row_ok ? __ldg(dsrc + i) : make_uint4(0, 0, 0, 0);
+                qw[4 * i] = a.x; qw[4 * i + 1] = a.y; qw[4 * i + 2] = a.z; qw[4 * i + 3] = a.w;
+                dw[4 * i] = b.x; dw[4 * i + 1] = b.y; dw[4 * i + 2] = b.z; dw[4 * i + 3] = b.w;
             }
+            tmem_st_32x32b_x16(t_q + lane_addr + oc * 16, qw);
+            tmem_st_32x32b_x16(t_do + lane_addr + oc * 16, dw);
+            uint32_t zero[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zero[i] = 0u;
+            tmem_st_32x32b_x32(t_dq + lane_addr + oc * 32, zero);   // every dQ MMA accumulates
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(ds_full);
+            mbar_arrive(qdo_full);
+        }
+        const float lse2 = row_ok ? p.LSE[(long long)head * p.n_q + q_row] * LOG2E : 0.f;
+        const float dlt = row_ok ? p.delta[(long long)head * p.n_q + q_row] : 0.f;
+        const uint32_t t_s = tmem_base + g * 128 + lane_addr + half * 32, t_dp = t_s + 64;
+        // invalid rows (beyond the segment) get lse = +inf so that exp2(s - lse) = 0 without a per-element select
+        const float neg_lse = row_ok ? -lse2 : -INFINITY;
+        // this thread's 64 bytes of dS row `row`: 16-byte chunks 4 half .. 4 half + 3, XOR-swizzled with (row & 7)
+        uint8_t* ds_row = ds_s + g * DS_BYTES + row * 128;
+        const int sw = row & 7;
+        long long w_sdp = 0, w_ld = 0, w_math = 0, w_st = 0, c_all0 = DBG_CLK();
+        for (int u = g; u < n_sub; u += 2) {
+            const uint32_t j = (uint32_t)(u >> 1);
+            long long c0 = DBG_CLK();
+            mbar_wait(&sdp_full[g], j & 1);
+            tc_fence_after();
+            long long c1 = DBG_CLK(); w_sdp += c1 - c0;
+            if (B200TTA_ATTN_DEBUG && (p.dbg_flags & 2)) {
+                tc_fence_before(); mbar_arrive(&sdp_free[g]); mbar_wait(&ds_free[g], (j & 1) ^ 1u); mbar_arrive(&ds_full[g]); continue;
+            }
+            const int valid = kv_len - u * SUB - half * 32;
+            uint32_t sv[32], dp[32], pk[16];
+            tmem_ld_32x32b_x32(t_s, sv);
+            tmem_ld_32x32b_x32(t_dp, dp);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&sdp_free[g]);   // S/dP(u + 2) may overwrite the buffer from here on
+            long long c2 = DBG_CLK(); w_ld += c2 - c1;
+            if (valid >= 32) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_lse));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_lse));
+                    pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - dlt), p1 * (__uint_as_float(dp[i + 1]) - dlt));
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = fast_exp2(fmaf(__uint_as_float(sv[i]), p.scale_log2, neg_lse));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, neg_lse));
+                    if (i >= valid) p0 = 0.f;
+                    if (i + 1 >= valid) p1 = 0.f;
+                    pk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - dlt), p1 * (__uint_as_float(dp[i + 1]) - dlt));
+                }
+            }
+            long long c3 = DBG_CLK(); w_math += c3 - c2;
+            mbar_wait(&ds_free[g], (j & 1) ^ 1u);   // dQ MMA of sub-block u - 2 has read the tile (first pass: fresh barrier)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(ds_row + (((half * 4 + c) ^ sw) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            fence_proxy_async();
+            mbar_arrive(&ds_full[g]);
+            w_st += DBG_CLK() - c3;
+        }
+        if (DBG_ON && warp == 3 && lane == 0) {
+            DBG_SET(4, DBG_CLK() - c_all0); DBG_SET(5, w_sdp); DBG_SET(6, w_ld); DBG_SET(7, 0); DBG_SET(8, w_math); DBG_SET(9, w_st);
         }
         mbar_wait(dq_done, 0);
         tc_fence_after();
-        store_row_bf16(p.dQ + (long long)q_row * p.lddq + head * D, t_dq + lane_addr, p.scale, row_ok);
+        // the four (group, half) combinations split the 128 output columns of the row
+        store_row_bf16(p.dQ + (long long)q_row * p.lddq + head * D, t_dq + lane_addr, p.scale, row_ok, oc, oc + 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -222,166 +374,215 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------ dK, dV
+// TMEM: buffer b: S^T at [128 b, 128 b + 64), dP^T at [128 b + 64, 128 b + 128); dV at [256, 384); dK at [384, 512).
 __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_constant__ BwdParams p) {
+    constexpr int STAGES = DKV_STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* k_s = smem;
     uint8_t* v_s = k_s + TILE_BYTES;
-    uint8_t* q_s = v_s + TILE_BYTES;               // [STAGES]
-    uint8_t* do_s = q_s + STAGES * TILE_BYTES;     // [STAGES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(do_s + STAGES * TILE_BYTES);
+    uint8_t* q_s = v_s + TILE_BYTES;               // [STAGES][SUBT_BYTES]
+    uint8_t* do_s = q_s + STAGES * SUBT_BYTES;     // [STAGES][SUBT_BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(do_s + STAGES * SUBT_BYTES);
     uint64_t* kv_full = bars;
     uint64_t* q_full = bars + 1;
     uint64_t* q_empty = q_full + STAGES;
     uint64_t* do_full = q_empty + STAGES;
     uint64_t* do_empty = do_full + STAGES;
-    uint64_t* sdp_full = do_empty + STAGES;
-    uint64_t* pds_full = sdp_full + 1;
-    uint64_t* dkv_done = pds_full + 1;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dkv_done + 1);
-    float* stat_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2 buffers][2][BT]
+    uint64_t* stat_full = do_empty + STAGES;
+    uint64_t* sdp_full = stat_full + STAGES;  // [2]
+    uint64_t* pds_full = sdp_full + 2;        // [2]
+    uint64_t* dkv_done = pds_full + 2;
+    uint64_t* acc_zero = dkv_done + 1;
+    uint64_t* turn = acc_zero + 1;            // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(turn + 2);
+    float* stat_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [STAGES][2][SUB]: LSE (log2), delta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kv0 = blockIdx.x * BT, head = blockIdx.y;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tma_q); tma_prefetch_desc(&p.tma_k); tma_prefetch_desc(&p.tma_v); tma_prefetch_desc(&p.tma_do);
+        tma_prefetch_desc(&p.tma_q64); tma_prefetch_desc(&p.tma_do64); tma_prefetch_desc(&p.tma_k128); tma_prefetch_desc(&p.tma_v128);
         mbar_init(kv_full, 1);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1);
+            mbar_init(&stat_full[i], 1);
         }
-        mbar_init(sdp_full, 1); mbar_init(pds_full, BT); mbar_init(dkv_done, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&sdp_full[b], 1); mbar_init(&pds_full[b], GROUP_THREADS); }
+        mbar_init(dkv_done, 2);
+        mbar_init(acc_zero, 2 * GROUP_THREADS);
+        mbar_init(&turn[0], 1); mbar_init(&turn[1], 1);
+        mbar_arrive(&turn[0]);   // issuer 0 has the first turn
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 384;
+    if (*tmem_ptr != 0) __trap();
+    constexpr uint32_t tmem_base = 0;
+    constexpr uint32_t t_dv = tmem_base + 256, t_dk = tmem_base + 384;
 
-    // every role walks the same list of query tiles: for each segment that can see this K/V block, its 128-row tiles
-    auto for_each_tile = [&](auto&& fn) {
-        int it = 0;
+    // every role walks the same list of 64-row query sub-tiles: for each segment that can see this K/V block
+    auto for_each_sub = [&](auto&& fn) {
+        int u = 0;
         for (int s = 0; s < p.n_seg; ++s) {
             if (kv0 >= p.seg_kv_len[s]) continue;
-            for (int q0 = p.seg_q_begin[s]; q0 < p.seg_q_end[s]; q0 += BT) fn(it++, s, q0);
+            for (int q0 = p.seg_q_begin[s]; q0 < p.seg_q_end[s]; q0 += SUB) fn(u++, s, q0);
         }
-        return it;
+        return u;
     };
+    int n_sub = 0;
+    for (int s = 0; s < p.n_seg; ++s)
+        if (kv0 < p.seg_kv_len[s]) n_sub += (p.seg_q_end[s] - p.seg_q_begin[s] + SUB - 1) / SUB;
 
     if (warp == 0) {
+        // whole warp: lane 0 drives TMA, all lanes stage the sub-tile's 64 LSE / delta values (two columns per lane)
         if (lane == 0) {
             mbar_arrive_expect_tx(kv_full, 2 * TILE_BYTES);
             for (int c = 0; c < 2; ++c) {
-                tma_load_2d(k_s + c * SUB_BYTES, &p.tma_k, kv_full, head * D + c * 64, kv0);
-                tma_load_2d(v_s + c * SUB_BYTES, &p.tma_v, kv_full, head * D + c * 64, kv0);
+                tma_load_2d(k_s + c * HALF_BYTES, &p.tma_k128, kv_full, head * D + c * 64, kv0);
+                tma_load_2d(v_s + c * HALF_BYTES, &p.tma_v128, kv_full, head * D + c * 64, kv0);
             }
-            for_each_tile([&](int it, int, int q0) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
-                mbar_wait(&q_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&q_full[stage], TILE_BYTES);
-                for (int c = 0; c < 2; ++c)
-                    tma_load_2d(q_s + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_q, &q_full[stage], head * D + c * 64, q0);
-                mbar_wait(&do_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&do_full[stage], TILE_BYTES);
-                for (int c = 0; c < 2; ++c)
-                    tma_load_2d(do_s + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_do, &do_full[stage], head * D + c * 64, q0);
-            });
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_kk = umma_idesc_bf16(BT, BT, 0, 0);
-            constexpr uint32_t idesc_mn = umma_idesc_bf16(BT, D, 0, 1);
-            mbar_wait(kv_full, 0);
-            const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
-            const int n_it = for_each_tile([&](int it, int, int) {
-                const int stage = it % STAGES;
-                const uint32_t phase = (it / STAGES) & 1;
-                const uint32_t qa = smem_u32(q_s + stage * TILE_BYTES), da = smem_u32(do_s + stage * TILE_BYTES);
-                mbar_wait(&q_full[stage], phase);
-                tc_fence_after();
-#pragma unroll
+        __syncwarp();
+        for_each_sub([&](int u, int s, int q0) {
+            const int st = u % STAGES;
+            const uint32_t ph = (u / STAGES) & 1;
+            // issue the global loads first: their latency overlaps the wait for the slot
+            const int qc = q0 + 2 * lane;
+            const int q_lim = p.seg_q_end[s];
+            const float* lse_g = p.LSE + (long long)head * p.n_q;
+            const float* dl_g = p.delta + (long long)head * p.n_q;
+            float2 l2, dl;   // exp2(-inf) = 0 masks the columns beyond the segment
+            l2.x = qc < q_lim ? __ldg(lse_g + qc) * LOG2E : INFINITY;
+            l2.y = qc + 1 < q_lim ? __ldg(lse_g + qc + 1) * LOG2E : INFINITY;
+            dl.x = qc < q_lim ? __ldg(dl_g + qc) : 0.f;
+            dl.y = qc + 1 < q_lim ? __ldg(dl_g + qc + 1) : 0.f;
+            // do_empty[st] / q_empty[st] complete after the MMAs of sub-tile u - STAGES, which were issued after every
+            // compute thread arrived on pds_full, i.e. after the last read of this slot's statistics
+            mbar_wait(&do_empty[st], ph ^ 1u);
+            mbar_wait(&q_empty[st], ph ^ 1u);
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&q_full[st], SUBT_BYTES);
                 for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(t_s, umma_desc_kmajor(ka + c * SUB_BYTES + ks * 32),
-                                umma_desc_kmajor(qa + c * SUB_BYTES + ks * 32), idesc_kk, (c | ks) ? 1u : 0u);
-                mbar_wait(&do_full[stage], phase);
-                tc_fence_after();
-#pragma unroll
+                    tma_load_2d(q_s + st * SUBT_BYTES + c * SUBH_BYTES, &p.tma_q64, &q_full[st], head * D + c * 64, q0);
+                mbar_arrive_expect_tx(&do_full[st], SUBT_BYTES);
                 for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(t_dp, umma_desc_kmajor(va + c * SUB_BYTES + ks * 32),
-                                umma_desc_kmajor(da + c * SUB_BYTES + ks * 32), idesc_kk, (c | ks) ? 1u : 0u);
-                umma_commit(sdp_full);
-                mbar_wait(pds_full, it & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ks = 0; ks < BT / 16; ++ks)
-                    umma_ts(t_dv, t_s + ks * 8, umma_desc_mnmajor(da + ks * 2048, SUB_BYTES), idesc_mn, (it | ks) ? 1u : 0u);
-                umma_commit(&do_empty[stage]);
-#pragma unroll
-                for (int ks = 0; ks < BT / 16; ++ks)
-                    umma_ts(t_dk, t_dp + ks * 8, umma_desc_mnmajor(qa + ks * 2048, SUB_BYTES), idesc_mn, (it | ks) ? 1u : 0u);
-                umma_commit(&q_empty[stage]);
-            });
-            (void)n_it;
-            umma_commit(dkv_done);
+                    tma_load_2d(do_s + st * SUBT_BYTES + c * SUBH_BYTES, &p.tma_do64, &do_full[st], head * D + c * 64, q0);
+            }
+            float* slot = stat_s + st * 2 * SUB;
+            *reinterpret_cast<float2*>(slot + 2 * lane) = l2;
+            *reinterpret_cast<float2*>(slot + SUB + 2 * lane) = dl;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stat_full[st]);
+        });
+    } else if (warp <= 2) {
+        // issuer w owns buffer w and the sub-tiles u = w, w+2, ...; whole warp converged, the elected lane issues
+        const int w = warp - 1;
+        mbar_wait(kv_full, 0);
+        mbar_wait(acc_zero, 0);
+        tc_fence_after();
+        const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
+        // strict turns between the two issuers, all waits before the turn is taken (see dq_kernel)
+        long long w_ds = 0, w_tot0 = DBG_CLK();
+        for (int k = w; k < n_sub + 2; k += 2) {
+            const int u = k - 2, un = k;
+            const int st_n = un % STAGES, st_u = (u + STAGES) % STAGES;
+            if (un < n_sub) mbar_wait2(&q_full[st_n], (un / STAGES) & 1, &do_full[st_n], (un / STAGES) & 1);
+            long long c0 = DBG_CLK();
+            if (u >= 0) mbar_wait2(&pds_full[w], (u >> 1) & 1, &turn[w], (k >> 1) & 1);
+            else mbar_wait(&turn[w], (k >> 1) & 1);
+            w_ds += DBG_CLK() - c0;
+            tc_fence_after();
+            if (u >= 0) {
+                mma_ts_k64(t_dv, tmem_base + w * 128, smem_u32(do_s + st_u * SUBT_BYTES));
+                umma_commit_e(&do_empty[st_u]);
+                mma_ts_k64(t_dk, tmem_base + w * 128 + 64, smem_u32(q_s + st_u * SUBT_BYTES));
+                umma_commit_e(&q_empty[st_u]);
+            }
+            if (un < n_sub) {
+                mma_ss_n64(tmem_base + w * 128, ka, smem_u32(q_s + st_n * SUBT_BYTES));
+                mma_ss_n64(tmem_base + w * 128 + 64, va, smem_u32(do_s + st_n * SUBT_BYTES));
+                umma_commit_e(&sdp_full[w]);
+            }
+            if (elect_one()) mbar_arrive(&turn[1 - w]);
         }
+        umma_commit_e(dkv_done);
+        if (DBG_ON && warp == 1 && lane == 0) { DBG_SET(16, DBG_CLK() - w_tot0); DBG_SET(17, w_ds); DBG_SET(18, (n_sub + 1) / 2); }
     } else {
+        const int g = (warp - 3) >> 3;
+        const int half = ((warp - 3) >> 2) & 1;   // query columns [32 half, 32 half + 32) of the 64-wide sub-tile
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;  // K/V row inside the block
         const int kv_row = kv0 + row;
         const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
-        const int tid = threadIdx.x - 64;  // 0..127
-        const int n_it = for_each_tile([&](int it, int s, int q0) {
-            // stage LSE (log2 units) and delta of this query tile: thread i loads column i
-            float* lse_s = stat_s + (it & 1) * 2 * BT;
-            float* dl_s = lse_s + BT;
-            {
-                const int qc = q0 + tid;
-                const bool ok = qc < p.seg_q_end[s];
-                lse_s[tid] = ok ? p.LSE[(long long)head * p.n_q + qc] * LOG2E : INFINITY;  // exp2(-inf) = 0 masks the column
-                dl_s[tid] = ok ? p.delta[(long long)head * p.n_q + qc] : 0.f;
-            }
-            named_bar_sync(1, BT);
+        const uint32_t t_s = tmem_base + g * 128 + lane_addr + half * 32, t_dp = t_s + 64;
+        {   // every dV / dK MMA accumulates: zero this thread's quarter of both accumulator rows
+            uint32_t zero[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zero[i] = 0u;
+            tmem_st_32x32b_x32(t_dv + lane_addr + (g * 2 + half) * 32, zero);
+            tmem_st_32x32b_x32(t_dk + lane_addr + (g * 2 + half) * 32, zero);
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(acc_zero);
+        }
+        long long w_sdp = 0, w_pre = 0, w_math = 0, w_st = 0, c_all0 = DBG_CLK();
+        for_each_sub([&](int u, int s, int) {
+            if ((u & 1) != g) return;
+            const int st = u % STAGES;
+            long long c0 = DBG_CLK();
             const bool row_ok = kv_row < p.seg_kv_len[s];
-            mbar_wait(sdp_full, it & 1);
+            const float row_bias = row_ok ? 0.f : -INFINITY;   // rows beyond the segment's kv_len contribute nothing
+            const bool all_rows = kv0 + BT <= p.seg_kv_len[s]; // block-uniform: the common case needs no row handling
+            const float* lse_s = stat_s + st * 2 * SUB + half * 32;
+            const float* dl_s = lse_s + SUB;
+            mbar_wait(&stat_full[st], (u / STAGES) & 1);
+            long long c1 = DBG_CLK(); w_pre += c1 - c0;
+            mbar_wait(&sdp_full[g], (u >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BT / 32; ++c) {
-                uint32_t st[32], dp[32], pk[16], dk[16];
-                tmem_ld_32x32b_x32(t_s + lane_addr + c * 32, st);
-                tmem_ld_32x32b_x32(t_dp + lane_addr + c * 32, dp);
+            long long c2 = DBG_CLK(); w_sdp += c2 - c1;
+            // two passes of 16 columns keep the live set under the 96-register budget of an 18-warp CTA; pass 1 stores
+            // over columns [8, 16), which pass 0 already consumed
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+                uint32_t sv[16], dp[16], pk[8], dk[8];
+                tmem_ld_32x32b_x16(t_s + hp * 16, sv);
+                tmem_ld_32x32b_x16(t_dp + hp * 16, dp);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float2 l2 = *reinterpret_cast<const float2*>(lse_s + c * 32 + i);
-                    const float2 dl = *reinterpret_cast<const float2*>(dl_s + c * 32 + i);
-                    float p0 = fast_exp2(fmaf(__uint_as_float(st[i]), p.scale_log2, -l2.x));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(st[i + 1]), p.scale_log2, -l2.y));
-                    if (!row_ok) { p0 = 0.f; p1 = 0.f; }
+                for (int i = 0; i < 16; i += 2) {
+                    const float2 l2 = *reinterpret_cast<const float2*>(lse_s + hp * 16 + i);
+                    const float2 dl = *reinterpret_cast<const float2*>(dl_s + hp * 16 + i);
+                    float a0 = fmaf(__uint_as_float(sv[i]), p.scale_log2, -l2.x);
+                    float a1 = fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -l2.y);
+                    if (!all_rows) { a0 += row_bias; a1 += row_bias; }
+                    const float p0 = fast_exp2(a0), p1 = fast_exp2(a1);
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - dl.x), p1 * (__uint_as_float(dp[i + 1]) - dl.y));
                 }
-                tmem_st_32x32b_x16(t_s + lane_addr + c * 16, pk);
-                tmem_st_32x32b_x16(t_dp + lane_addr + c * 16, dk);
+                tmem_st_32x32b_x8(t_s + hp * 8, pk);     // P^T  (bf16) over S^T columns this thread already loaded
+                tmem_st_32x32b_x8(t_dp + hp * 8, dk);    // dS^T (bf16) likewise over dP^T
             }
+            long long c3 = DBG_CLK(); w_math += c3 - c2;
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(pds_full);
+            mbar_arrive(&pds_full[g]);
+            w_st += DBG_CLK() - c3;
         });
+        if (DBG_ON && warp == 3 && lane == 0) {
+            DBG_SET(20, DBG_CLK() - c_all0); DBG_SET(21, w_sdp); DBG_SET(22, w_pre); DBG_SET(23, w_math); DBG_SET(24, w_st);
+        }
         mbar_wait(dkv_done, 0);
         tc_fence_after();
         const bool ok = kv_row < p.n_kv;
-        if (n_it > 0) {
-            store_row_bf16(p.dV + (long long)kv_row * p.lddv + head * D, t_dv + lane_addr, 1.0f, ok);
-            store_row_bf16(p.dK + (long long)kv_row * p.lddk + head * D, t_dk + lane_addr, p.scale, ok);
+        const int oc = g * 2 + half;
+        if (n_sub > 0) {
+            store_row_bf16(p.dV + (long long)kv_row * p.lddv + head * D, t_dv + lane_addr, 1.0f, ok, oc, oc + 1);
+            store_row_bf16(p.dK + (long long)kv_row * p.lddk + head * D, t_dk + lane_addr, p.scale, ok, oc, oc + 1);
         } else if (ok) {  // a K/V block no query sees: gradients are zero
-            for (int c = 0; c < D / 8; ++c) {
+            for (int c = oc * 4; c < oc * 4 + 4; ++c) {
                 *reinterpret_cast<uint4*>(p.dV + (long long)kv_row * p.lddv + head * D + c * 8) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(p.dK + (long long)kv_row * p.lddk + head * D + c * 8) = make_uint4(0, 0, 0, 0);
             }
@@ -396,6 +597,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
 }  // namespace b200
 
 using namespace b200;
+
+#if B200TTA_ATTN_DEBUG
+extern "C" int b200tta_debug_read(long long* out32) {
+    return cudaMemcpyFromSymbol(out32, g_dbg, sizeof(long long) * 32) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
                                 int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
@@ -413,15 +620,20 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
     cudaStream_t st = (cudaStream_t)stream;
     BwdParams p;
     memset(&p, 0, sizeof(p));
-    if (int rc = make_tmap_2d_bf16(&p.tma_q, Q, (uint64_t)heads * D, (uint64_t)n_q, (uint64_t)ldq * 2, 64, BT)) return rc;
-    if (int rc = make_tmap_2d_bf16(&p.tma_do, dO, (uint64_t)heads * D, (uint64_t)n_q, (uint64_t)lddo * 2, 64, BT)) return rc;
-    if (int rc = make_tmap_2d_bf16(&p.tma_k, K, (uint64_t)heads * D, (uint64_t)n_kv, (uint64_t)ldk * 2, 64, BT)) return rc;
-    if (int rc = make_tmap_2d_bf16(&p.tma_v, V, (uint64_t)heads * D, (uint64_t)n_kv, (uint64_t)ldv * 2, 64, BT)) return rc;
+    const uint64_t inner = (uint64_t)heads * D;
+    if (int rc = make_tmap_2d_bf16(&p.tma_k128, K, inner, (uint64_t)n_kv, (uint64_t)ldk * 2, 64, BT)) return rc;
+    if (int rc = make_tmap_2d_bf16(&p.tma_v128, V, inner, (uint64_t)n_kv, (uint64_t)ldv * 2, 64, BT)) return rc;
+    if (int rc = make_tmap_2d_bf16(&p.tma_q64, Q, inner, (uint64_t)n_q, (uint64_t)ldq * 2, 64, SUB)) return rc;
+    if (int rc = make_tmap_2d_bf16(&p.tma_do64, dO, inner, (uint64_t)n_q, (uint64_t)lddo * 2, 64, SUB)) return rc;
+    if (int rc = make_tmap_2d_bf16(&p.tma_k64, K, inner, (uint64_t)n_kv, (uint64_t)ldk * 2, 64, SUB)) return rc;
+    if (int rc = make_tmap_2d_bf16(&p.tma_v64, V, inner, (uint64_t)n_kv, (uint64_t)ldv * 2, 64, SUB)) return rc;
+    p.Q = (const __nv_bfloat16*)Q; p.dO = (const __nv_bfloat16*)dO; p.ldq = ldq; p.lddo = lddo;
     p.dQ = (__nv_bfloat16*)dQ; p.dK = (__nv_bfloat16*)dK; p.dV = (__nv_bfloat16*)dV;
     p.lddq = lddq; p.lddk = lddk; p.lddv = lddv;
     p.LSE = LSE; p.delta = delta; p.n_q = n_q; p.n_kv = n_kv; p.heads = heads;
     p.scale = softmax_scale; p.scale_log2 = softmax_scale * LOG2E;
     p.n_seg = n_seg;
+    if (B200TTA_ATTN_DEBUG && getenv("B200TTA_DEBUG_FLAGS")) p.dbg_flags = atoi(getenv("B200TTA_DEBUG_FLAGS"));
     int items = 0;
     for (int s = 0; s < n_seg; ++s) {
         B200_REQUIRE(segs[s].q_begin >= 0 && segs[s].q_end > segs[s].q_begin && segs[s].q_end <= n_q &&
@@ -434,8 +646,8 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
     p.seg_item0[n_seg] = items;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        B200_CUDA(cudaFuncSetAttribute(dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        B200_CUDA(cudaFuncSetAttribute(dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DQ_SMEM_BYTES));
+        B200_CUDA(cudaFuncSetAttribute(dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DKV_SMEM_BYTES));
         attr = true;
     }
     {
@@ -444,9 +656,9 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
                                                                           (const __nv_bfloat16*)O, ldo, n_q, heads);
         B200_LAUNCHED();
     }
-    dq_kernel<<<dim3(items, heads), NUM_THREADS, SMEM_BYTES, st>>>(p);
+    if (!B200TTA_ATTN_DEBUG || !getenv("B200TTA_DEBUG_NO_DQ")) dq_kernel<<<dim3(items, heads), NUM_THREADS, DQ_SMEM_BYTES, st>>>(p);
     B200_LAUNCHED();
-    dkv_kernel<<<dim3((n_kv + BT - 1) / BT, heads), NUM_THREADS, SMEM_BYTES, st>>>(p);
+    if (!B200TTA_ATTN_DEBUG || !getenv("B200TTA_DEBUG_NO_DKV")) dkv_kernel<<<dim3((n_kv + BT - 1) / BT, heads), NUM_THREADS, DKV_SMEM_BYTES, st>>>(p);
     B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -93,8 +93,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_s0 = tmem_base, tmem_o0 = tmem_base + TILES * BN;
+    // the CTA owns all 512 TMEM columns (one CTA per SM by shared-memory footprint), so the allocation starts at
+    // column 0 / lane 0: use the constant so that MMA operand addresses are compile-time uniform values
+    if (*tmem_ptr != 0) __trap();
+    constexpr uint32_t tmem_base = 0;
+    constexpr uint32_t tmem_s0 = tmem_base, tmem_o0 = tmem_base + TILES * BN;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -118,33 +121,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (whole warp converged, elected lane issues)
+        {
             constexpr uint32_t idesc_s = umma_idesc_bf16(BM, BN, 0, 0);  // S = Q K^T : both K-major
             constexpr uint32_t idesc_o = umma_idesc_bf16(BM, D, 0, 1);   // O += P V  : A in TMEM, B = V MN-major
+            const uint32_t q_base = smem_u32(q_smem), k_base = smem_u32(k_smem), v_base = smem_u32(v_smem);
             auto issue_s = [&](int t, int kstage) {
-                const uint32_t qa = smem_u32(q_smem + t * TILE_BYTES), ka = smem_u32(k_smem + kstage * TILE_BYTES);
+                const uint64_t qd = umma_desc_kmajor(q_base + t * TILE_BYTES), kd = umma_desc_kmajor(k_base + kstage * TILE_BYTES);
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_ss(tmem_s0 + t * BN, umma_desc_kmajor(qa + c * SUB_BYTES + ks * 32),
-                                umma_desc_kmajor(ka + c * SUB_BYTES + ks * 32), idesc_s, (c | ks) ? 1u : 0u);
-                umma_commit(&s_full[t]);
+                        umma_ss_e(tmem_s0 + t * BN, umma_desc_advance(qd, c * SUB_BYTES + ks * 32),
+                                  umma_desc_advance(kd, c * SUB_BYTES + ks * 32), idesc_s, (c | ks) ? 1u : 0u);
+                umma_commit_e(&s_full[t]);
             };
             auto issue_pv = [&](int t, int vstage, bool accumulate) {
-                const uint32_t va = smem_u32(v_smem + vstage * TILE_BYTES);
+                const uint64_t vd = umma_desc_mnmajor(v_base + vstage * TILE_BYTES, SUB_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < BN / 16; ++ks)
-                    umma_ts(tmem_o0 + t * D, tmem_s0 + t * BN + ks * 8, umma_desc_mnmajor(va + ks * 2048, SUB_BYTES),
-                            idesc_o, (accumulate || ks) ? 1u : 0u);
+                    umma_ts_e(tmem_o0 + t * D, tmem_s0 + t * BN + ks * 8, umma_desc_advance(vd, ks * 2048),
+                              idesc_o, (accumulate || ks) ? 1u : 0u);
             };
             mbar_wait(q_full, 0);
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
             issue_s(0, 0);
             issue_s(1, 0);
-            umma_commit(&k_empty[0]);
+            umma_commit_e(&k_empty[0]);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_blocks; ++j) {
@@ -156,13 +160,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                     mbar_wait(&p_full[t], j & 1);
                     tc_fence_after();
                     issue_pv(t, stage, j > 0);
-                    if (t == TILES - 1) umma_commit(&v_empty[stage]);
+                    if (t == TILES - 1) umma_commit_e(&v_empty[stage]);
                     if (j + 1 < n_blocks) {
                         if (t == 0) { mbar_wait(&k_full[nstage], nphase); tc_fence_after(); }
                         issue_s(t, nstage);
-                        if (t == TILES - 1) umma_commit(&k_empty[nstage]);
+                        if (t == TILES - 1) umma_commit_e(&k_empty[nstage]);
                     } else {
-                        umma_commit(&o_done[t]);
+                        umma_commit_e(&o_done[t]);
                     }
                 }
                 stage = nstage;
@@ -183,20 +187,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             mbar_wait(&s_full[t], j & 1);
             tc_fence_after();
             const int valid = kv_len - j * BN;  // columns >= valid are masked (only on the last block)
-            // pass 1: block row maximum (log2 units)
-            float mb = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(s_addr + c * 32, r);
-                tmem_ld_wait();
+            // the whole 128-column row of S in registers: four back-to-back TMEM loads, one wait
+            uint32_t sr[4][32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = __uint_as_float(r[i]);
-                    if (c * 32 + i < valid) mb = fmaxf(mb, s);
-                }
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr[c]);
+            tmem_ld_wait();
+            // block row maximum (log2 units), four independent chains for ILP
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            if (valid >= BN) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx[c] = fmaxf(mx[c], __uint_as_float(sr[c][i]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < valid) mx[c] = fmaxf(mx[c], __uint_as_float(sr[c][i]));
             }
-            mb *= p.scale_log2;
+            float mb = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;
             // stale-maximum online softmax: only move the reference maximum when it grew by > threshold
             float alpha = 1.0f;
             const bool grow = mb > m + RESCALE_THRESHOLD;
@@ -217,25 +227,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                 }
                 tmem_st_wait();
             }
-            // pass 2: P = exp2(s * scale - m) -> bf16 pairs over the first half of S_t
+            // P = exp2(s * scale - m) -> bf16 pairs over the first half of S_t
             const float neg_m = -m;
-            float lsum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32], pk[16];
-                tmem_ld_32x32b_x32(s_addr + c * 32, r);
-                tmem_ld_wait();
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = fast_exp2(fmaf(__uint_as_float(r[i]), p.scale_log2, neg_m));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, neg_m));
-                    if (c * 32 + i >= valid) p0 = 0.f;
-                    if (c * 32 + i + 1 >= valid) p1 = 0.f;
-                    lsum += p0 + p1;
+                    float p0 = fast_exp2(fmaf(__uint_as_float(sr[c][i]), p.scale_log2, neg_m));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(sr[c][i + 1]), p.scale_log2, neg_m));
+                    if (valid < BN) {
+                        if (c * 32 + i >= valid) p0 = 0.f;
+                        if (c * 32 + i + 1 >= valid) p1 = 0.f;
+                    }
+                    ls[c] += p0 + p1;
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                 }
                 tmem_st_32x32b_x16(s_addr + c * 16, pk);
             }
+            const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
             l += lsum;
             tmem_st_wait();
             tc_fence_before();

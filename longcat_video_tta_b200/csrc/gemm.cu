@@ -241,10 +241,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------ MMA issuer (whole warp converged, elected lane issues)
+        {
             constexpr uint32_t idesc_k = umma_idesc_bf16(BM, BN, 0, 0);
             constexpr uint32_t idesc_mn = umma_idesc_bf16(BM, BN, 0, 1);
+            const uint32_t smem_base = smem_u32(smem);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -259,28 +260,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+                        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
                         const uint32_t sb = sa + C::A_BYTES;
                         const int rem = p.k[s] - kb * BK;
                         const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                        const uint64_t ad = umma_desc_kmajor(sa);
                         if (p.b_mn[s]) {
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                umma_ss(d_tmem, umma_desc_kmajor(sa + ks * 32),
-                                        umma_desc_mnmajor(sb + ks * 2048, 64 * BK * 2), idesc_mn, accumulate);
-                                accumulate = 1;
+                            const uint64_t bd = umma_desc_mnmajor(sb, 64 * BK * 2);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    umma_ss_e(d_tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 2048), idesc_mn, accumulate);
+                                    accumulate = 1;
+                                }
                             }
                         } else {
-                            for (int ks = 0; ks < ksteps; ++ks) {
-                                umma_ss(d_tmem, umma_desc_kmajor(sa + ks * 32), umma_desc_kmajor(sb + ks * 32), idesc_k,
-                                        accumulate);
-                                accumulate = 1;
+                            const uint64_t bd = umma_desc_kmajor(sb);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    umma_ss_e(d_tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_k, accumulate);
+                                    accumulate = 1;
+                                }
                             }
                         }
-                        umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+                        umma_commit_e(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
-                umma_commit(&tmem_full[acc]);
+                umma_commit_e(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }

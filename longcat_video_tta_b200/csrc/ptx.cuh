@@ -69,6 +69,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// wait for two barriers with both polls in flight at once (a poll from an MMA-issuing thread costs ~100 clk)
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+    uint32_t spins = 0;
+    bool a = false, b = false;
+    while (true) {
+        const bool ta = a || mbar_try_wait(bar_a, parity_a);
+        const bool tb = b || mbar_try_wait(bar_b, parity_b);
+        a = ta; b = tb;
+        if (a && b) break;
+        if (++spins > B200TTA_SPIN_LIMIT) {
+            printf("b200tta: mbarrier timeout block %d thread %d bars %p/%p\n", (int)blockIdx.x, (int)threadIdx.x,
+                   (void*)bar_a, (void*)bar_b);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -136,10 +153,23 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Warp-converged issue (the whole MMA warp executes the surrounding loop so that ptxas keeps descriptors and TMEM
+// addresses in uniform registers; only the instruction itself is predicated on the elected lane).  Issuing from inside
+// a divergent `if (lane == 0)` costs ~100 cycles per MMA in R2UR moves and a waterfall loop (round-1 finding).
+__device__ __forceinline__ void umma_ss_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) umma_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (elect_one()) umma_ts(d_tmem, a_tmem, b_desc, idesc, accumulate);
+}
 // all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+    if (elect_one()) umma_commit(bar);
 }
 
 // TMEM -> registers, 32 lanes x 32 bit, N consecutive columns (thread i of the warp <-> lane base+i)
@@ -185,6 +215,12 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
@@ -206,6 +242,13 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
 __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t smem_addr, uint32_t chunk_stride_bytes) {
     return kDescSw128 | (uint64_t(1024 >> 4) << 32) | (uint64_t(chunk_stride_bytes >> 4) << 16) |
            uint64_t((smem_addr & 0x3FFFF) >> 4);
+}
+
+// Advance a descriptor by a byte offset inside the same tile: only the 14-bit start-address field (units of 16 B) of
+// the low word changes, so one 32-bit add per k-step replaces rebuilding the descriptor (~10 uniform ALU ops).
+__device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t byte_offset) {
+    const uint32_t lo = static_cast<uint32_t>(desc) + (byte_offset >> 4);
+    return (desc & 0xFFFFFFFF00000000ull) | lo;
 }
 
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32.

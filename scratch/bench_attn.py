@@ -30,3 +30,26 @@ with torch.no_grad():
     ref = torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), v[:, hs].float())
     err = (o[qs, hs].float() - ref).abs().max().item()
     print(f"fwd spot-check max err {err:.4g} (ref max {ref.abs().max().item():.3g})")
+import ctypes as C
+from longcat_video_tta_b200 import _lib
+lib = _lib.load()
+buf = (C.c_longlong * 32)()
+if not hasattr(lib, "b200tta_debug_read"):
+    sys.exit(0)   # library built without -DB200TTA_ATTN_DEBUG=1
+lib.b200tta_debug_read.argtypes = [C.c_void_p]
+if lib.b200tta_debug_read(buf) == 0:
+    d = list(buf)
+    n = max(d[2], 1)
+    print(f"dq CTA(0,0): issuer own-subs {d[2]}; issuer total {d[0]} clk ({d[0]/n:.0f}/own-sub), waiting ds_full {d[1]/n:.0f}, k/v_full {d[3]/n:.0f}, sdp_free {d[10]/n:.0f}")
+    m = n
+    print(f"  compute warp2: total {d[4]} ({d[4]/m:.0f}/own-sub): wait sdp {d[5]/m:.0f}, tmem ld {d[6]/m:.0f}, math {d[8]/m:.0f}, st+arrive {d[9]/m:.0f}")
+    n = max(d[18], 1); m = n
+    print(f"dkv CTA(0,0): n_sub {d[18]}; MMA thread total {d[16]} clk ({d[16]/n:.0f}/sub), waiting pds_full {d[17]/n:.0f}/sub")
+    print(f"  compute warp2: total {d[20]} ({d[20]/m:.0f}/own-sub): wait sdp {d[21]/m:.0f}, pre {d[22]/m:.0f}, ld+bar+math {d[23]/m:.0f}, st+arrive {d[24]/m:.0f}")
+import os
+if not os.environ.get("B200TTA_DEBUG_NO_DQ") and not os.environ.get("B200TTA_DEBUG_NO_DKV"):
+    for var in ("B200TTA_DEBUG_NO_DQ", "B200TTA_DEBUG_NO_DKV"):
+        os.environ[var] = "1"
+        t = timeit(lambda: ops.attn_bwd(dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], do, o, lse, delta, q, k, v, segs, D ** -0.5))
+        print(f"{var}: {t:.2f} ms")
+        del os.environ[var]
