@@ -34,15 +34,22 @@ import ctypes as C
 from longcat_video_tta_b200 import _lib
 lib = _lib.load()
 buf = (C.c_longlong * 32)()
+if hasattr(lib, "b200tta_debug_read_fwd"):
+    lib.b200tta_debug_read_fwd.argtypes = [C.c_void_p]
+    if lib.b200tta_debug_read_fwd(buf) == 0:
+        d = list(buf); n = max(d[3], 1)
+        print(f"fwd CTA(0,0): n_blocks {d[3]}; issuer {d[0]/n:.0f} clk/block (wait p_full {d[1]/n:.0f}, k/v_full {d[2]/n:.0f})")
+        for off, nm in ((8, "tile0"), (16, "tile1")):
+            print(f"  softmax {nm}: {d[off]/n:.0f}/block: wait s_full {d[off+1]/n:.0f}, tmem ld {d[off+2]/n:.0f}, max(+rescale) {d[off+3]/n:.0f}, exp+st+arrive {d[off+4]/n:.0f}")
 if not hasattr(lib, "b200tta_debug_read"):
     sys.exit(0)   # library built without -DB200TTA_ATTN_DEBUG=1
 lib.b200tta_debug_read.argtypes = [C.c_void_p]
 if lib.b200tta_debug_read(buf) == 0:
     d = list(buf)
     n = max(d[2], 1)
-    print(f"dq CTA(0,0): issuer own-subs {d[2]}; issuer total {d[0]} clk ({d[0]/n:.0f}/own-sub), waiting ds_full {d[1]/n:.0f}, k/v_full {d[3]/n:.0f}, sdp_free {d[10]/n:.0f}")
+    print(f"dq CTA(0,0): issuer own-subs {d[2]}; issuer total {d[0]} clk ({d[0]/n:.0f}/own-sub), waiting ds_full {d[1]/n:.0f}, v_full {d[3]/n:.0f}, s_free+k {d[10]/n:.0f}")
     m = n
-    print(f"  compute warp2: total {d[4]} ({d[4]/m:.0f}/own-sub): wait sdp {d[5]/m:.0f}, tmem ld {d[6]/m:.0f}, math {d[8]/m:.0f}, st+arrive {d[9]/m:.0f}")
+    print(f"  compute warp2: total {d[4]} ({d[4]/m:.0f}/own-sub): wait s_full {d[5]/m:.0f}, ld S+exp {d[8]/m:.0f}, wait dp_full+ld {d[6]/m:.0f}, ds+st {d[9]/m:.0f}")
     n = max(d[18], 1); m = n
     print(f"dkv CTA(0,0): n_sub {d[18]}; MMA thread total {d[16]} clk ({d[16]/n:.0f}/sub), waiting pds_full {d[17]/n:.0f}/sub")
     print(f"  compute warp2: total {d[20]} ({d[20]/m:.0f}/own-sub): wait sdp {d[21]/m:.0f}, pre {d[22]/m:.0f}, ld+bar+math {d[23]/m:.0f}, st+arrive {d[24]/m:.0f}")
