@@ -276,7 +276,8 @@ def run_b200(args):
         "config": {"workload": WORKLOAD if cfg_name == "13.6b" and (Tc, Tt, Hl, Wl, M) == (4, 20, 60, 104, 512) else
                    f"{cfg_name} LoRA r=16 TTA step, latent [16,{Tc}+{Tt},{Hl},{Wl}], {M} text tokens",
                    "tokens": geo.N, "adapter_params": stepper.n_params, "parallelism": f"dp{world} over noise draws",
-                   "recompute": "per-block forward re-run in the backward except self-attention (O, LSE kept for all blocks)",
+                   "recompute": "per-block forward re-run in the backward except self-attention (O, LSE kept for all blocks) "
+                                "and whatever fits the spare-HBM activation stash (blocks covered: " + _stash_summary(stepper.eng) + ")",
                    "l2": "inputs far exceed L2: 27 GB of frozen weights + 15 GB of block inputs are streamed every step"},
         "clocks": clocks,
         "e2e": {"value": world / (ms_e2e / args.steps / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -326,6 +327,13 @@ def _family(name, a):
     if fam == "lora_linear_bwd":
         return "linear_bwd (tcgen05 GEMM dX + LoRA grads)"
     return fam
+
+
+def _stash_summary(eng):
+    st = getattr(eng, "_stash", None)
+    if not st:
+        return "none"
+    return ", ".join(f"{k[2:]} {st[k]}/{eng.L}" for k in ("k_x1", "k_x2", "k_qkv", "k_h"))
 
 
 def profile_step(ops, fn):

@@ -14,11 +14,15 @@ What is saved where (HBM layout, N tokens, C hidden, F ffn):
   o_all[L][N,C], lse_all[L][H,N]   self-attention output and log-sum-exp of every block (the recompute pass skips attention)
   ws.*                   one block's intermediates: xm1, qkv, qk(normed+roped), x1, xn, qc, qcn, kvc, kcn, oc,
                          lsec, x2, xm2, h1, h3, h and the gradient temporaries; re-used by every block
+  stash (optional)       whatever HBM is left after the above (180 GB per B200) keeps, for as many blocks as fit,
+                         x1 / x2 [N,C], qkv [N,3C] and h1,h3 [N,F] of the training forward, so the recompute pass skips
+                         the GEMMs that produced them (same values, bit for bit); the w2 GEMM is never re-run
   grad_flat f32          all adapter gradients back to back (LoRA "down" gradients transposed, see b200tta.h)
 """
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -211,6 +215,8 @@ class TTAEngine:
         self._site_sig = None
         self.grad_flat: Optional[torch.Tensor] = None
         self._text_cache = None
+        self._stash = None          # activation stash of the training geometry (see _ensure_stash)
+        self._stash_on = False      # the forward in flight writes / the recompute reads the stash
         self.device = dit.x_embedder.proj.weight.device
         if dit.x_embedder.proj.weight.dtype != BF16:
             raise TypeError("B200DiT parameters must be bf16 (the kernels read them in place)")
@@ -269,6 +275,16 @@ class TTAEngine:
             return
         if len(cache) >= 2:
             cache.clear()
+        try:
+            self._plan_new(geo, cache)
+        except torch.OutOfMemoryError:
+            # the activation stash of another geometry took the memory: it is an optimisation, give it back
+            self._release_stash()
+            self.ws = None
+            torch.cuda.empty_cache()
+            self._plan_new(geo, cache)
+
+    def _plan_new(self, geo: Geometry, cache):
         self.geo = geo
         dev, C, F, H = self.device, self.C, self.F, self.H
         N, Nn, M, T = geo.N, geo.Nn, geo.M, geo.T
@@ -283,16 +299,17 @@ class TTAEngine:
         ws.y1, ws.y = e(M, C), e(M, C)
         ws.mod, ws.modf = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32)
         ws.xm1, ws.xm2 = e(N, C), e(N, C)
-        ws.qkv, ws.qk = e(N, 3 * C), e(N, 2 * C)
+        ws.qkv_tmp, ws.qk = e(N, 3 * C), e(N, 2 * C)
         # self-attention output + log-sum-exp are kept for EVERY block (312 MB per block at 37k tokens) so that the
         # per-block recompute in the backward never re-runs the attention forward (the most expensive op to redo)
         ws.o_all, ws.lse_all = e(self.L, N, C), e(self.L, H, N, dt=F32)
         ws.delta = e(H, N, dt=F32)
-        ws.x1, ws.x2 = e(N, C), e(N, C)
+        ws.x1_tmp, ws.x2_tmp = e(N, C), e(N, C)
         ws.xn, ws.qc, ws.qcn, ws.oc = e(Nn, C), e(Nn, C), e(Nn, C), e(Nn, C)
         ws.kvc, ws.kcn = e(M, 2 * C), e(M, C)
         ws.lsec, ws.deltac = e(H, Nn, dt=F32), e(H, Nn, dt=F32)
-        ws.h, ws.h1, ws.h3 = e(N, F), e(N, F), e(N, F)
+        ws.h, ws.h1_tmp, ws.h3_tmp = e(N, F), e(N, F), e(N, F)
+        ws.qkv, ws.x1, ws.x2, ws.h1, ws.h3 = ws.qkv_tmp, ws.x1_tmp, ws.x2_tmp, ws.h1_tmp, ws.h3_tmp
         ws.xf, ws.pred = e(N, C), e(N, 64, dt=F32)
         # backward temporaries
         ws.dx = e(N, C)
@@ -307,6 +324,53 @@ class TTAEngine:
         self.ws = ws
         cache[geo] = ws
         self._alloc_lora_ws()
+
+    # ------------------------------------------------------------------ activation stash
+    def _release_stash(self):
+        self._stash = None
+        self._stash_on = False
+
+    def _ensure_stash(self, geo: Geometry):
+        """Spend the HBM that is still free on per-block activations of the training forward (x1, x2, qkv, h1/h3, in
+        that order, each for as many leading blocks as fit).  B200TTA_STASH_GB caps it (0 disables); 12 GB stay free."""
+        if self._stash is not None and self._stash["geo"] == geo:
+            return
+        self._release_stash()
+        torch.cuda.empty_cache()
+        free, _ = torch.cuda.mem_get_info(self.device)
+        budget = free - (12 << 30)
+        cap = os.environ.get("B200TTA_STASH_GB")
+        if cap is not None:
+            budget = min(budget, int(float(cap) * (1 << 30)))
+        N, C, F, L = geo.N, self.C, self.F, self.L
+        st = {"geo": geo}
+        for name, cols, parts in (("x1", C, 1), ("x2", C, 1), ("qkv", 3 * C, 1), ("h", F, 2)):
+            per_block = N * cols * 2 * parts
+            k = int(max(0, min(L, budget // per_block)))
+            budget -= k * per_block
+            st["k_" + name] = k
+            st[name] = torch.empty(k, parts, N, cols, dtype=BF16, device=self.device) if k else None
+        self._stash = st
+
+    def _bind(self, b: int):
+        """Point the per-block workspace names at block b's slots."""
+        ws, st = self.ws, self._stash if self._stash_on else None
+        ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
+        ws.x1 = st["x1"][b, 0] if st and b < st["k_x1"] else ws.x1_tmp
+        ws.x2 = st["x2"][b, 0] if st and b < st["k_x2"] else ws.x2_tmp
+        ws.qkv = st["qkv"][b, 0] if st and b < st["k_qkv"] else ws.qkv_tmp
+        if st and b < st["k_h"]:
+            ws.h1, ws.h3 = st["h"][b, 0], st["h"][b, 1]
+        else:
+            ws.h1, ws.h3 = ws.h1_tmp, ws.h3_tmp
+
+    def _stashed(self, b: int, name: str) -> bool:
+        return self._stash_on and self._stash is not None and b < self._stash["k_" + name]
+
+    def _xa_only(self, s, x, nm):
+        """recompute pass, output already stashed: only the LoRA down-projection x A^T is needed (for dB)."""
+        if s.has_lora:
+            ops.lora_down(self._xa(s, nm, x.shape[0]), x, s.A, scale=s.scale)
 
     def _alloc_lora_ws(self):
         ws, geo = self.ws, self.geo
@@ -399,7 +463,7 @@ class TTAEngine:
     # ------------------------------------------------------------------ block forward
     def _block_fwd(self, b: int, x_in, x_out, ex: Optional[Extras], recompute: bool = False):
         ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
-        ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
+        self._bind(b)
         blk, st = self.dit.blocks[b], self.sites[b]
         N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
         ada = blk.adaLN_modulation[1]
@@ -417,7 +481,10 @@ class TTAEngine:
         # ---- self attention
         ops.ln_mod_fwd(ws.xm1, x_in, scale_msa, shift_msa, tokens_per_frame=tpf)
         s = st["qkv"]
-        self._linear_fwd_xa(s, ws.xm1, ops.epi(ops.EPI_STORE, ws.qkv, bias=s.bias), "qkv")
+        if recompute and self._stashed(b, "qkv"):
+            self._xa_only(s, ws.xm1, "qkv")
+        else:
+            self._linear_fwd_xa(s, ws.xm1, ops.epi(ops.EPI_STORE, ws.qkv, bias=s.bias), "qkv")
         ops.qk_rmsnorm_rope_fwd(ws.qk, ws.qkv, blk.attn.q_norm.weight, blk.attn.k_norm.weight, H, H,
                                 grid_hw=(geo.gh, geo.gw), rope_base=self.dit.config.rope_base)
         q = ws.qk.view(N, 2 * H, D)[:, :H]
@@ -426,8 +493,11 @@ class TTAEngine:
         if not recompute:
             ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
         s = st["proj"]
-        self._linear_fwd_xa(s, ws.o, ops.epi(ops.EPI_GATE_RESID, ws.x1, bias=s.bias, resid=x_in, gate=gate_msa,
-                                             tokens_per_frame=tpf, d2=ws.branch_a if keep_branch else None), "proj")
+        if recompute and self._stashed(b, "x1") and not keep_branch:
+            self._xa_only(s, ws.o, "proj")
+        else:
+            self._linear_fwd_xa(s, ws.o, ops.epi(ops.EPI_GATE_RESID, ws.x1, bias=s.bias, resid=x_in, gate=gate_msa,
+                                                 tokens_per_frame=tpf, d2=ws.branch_a if keep_branch else None), "proj")
         # ---- cross attention (noise tokens only; context rows pass through)
         if Nn > 0:
             nrm = blk.pre_crs_attn_norm
@@ -441,25 +511,40 @@ class TTAEngine:
             vc = ws.kvc.view(M, 2 * H, D)[:, H:]
             ops.attn_fwd(ws.qcn.view(Nn, H, D), ws.kcn.view(M, H, D), vc, ws.oc.view(Nn, H, D), ws.lsec,
                          [(0, Nn, M)], self.softmax_scale)
-            if Nc > 0:
-                ws.x2[:Nc].copy_(ws.x1[:Nc])
             s = st["cproj"]
-            self._linear_fwd_xa(s, ws.oc, ops.epi(ops.EPI_GATE_RESID, ws.x2[Nc:], bias=s.bias, resid=ws.x1[Nc:]), "cproj")
-        else:
+            if recompute and self._stashed(b, "x2"):
+                self._xa_only(s, ws.oc, "cproj")
+            else:
+                if Nc > 0:
+                    ws.x2[:Nc].copy_(ws.x1[:Nc])
+                self._linear_fwd_xa(s, ws.oc, ops.epi(ops.EPI_GATE_RESID, ws.x2[Nc:], bias=s.bias, resid=ws.x1[Nc:]), "cproj")
+        elif not (recompute and self._stashed(b, "x2")):
             ws.x2.copy_(ws.x1)
         # ---- FFN
-        ops.ln_mod_fwd(ws.xm2, ws.x2, scale_mlp, shift_mlp, tokens_per_frame=tpf)
         s1, s3, s2 = st["w1"], st["w3"], st["w2"]
+        # the recompute pass never needs the block output (xs[b+1] is kept): w2 only re-runs for its own LoRA / FiLM needs
+        need_w2 = (not recompute) or keep_branch or s2.has_lora
+        h_stashed = recompute and self._stashed(b, "h")
+        if not h_stashed or s1.has_lora or s3.has_lora:
+            ops.ln_mod_fwd(ws.xm2, ws.x2, scale_mlp, shift_mlp, tokens_per_frame=tpf)
         if s1.has_lora or s3.has_lora:
-            self._linear_fwd_xa(s1, ws.xm2, ops.epi(ops.EPI_STORE, ws.h1), "w1")
-            self._linear_fwd_xa(s3, ws.xm2, ops.epi(ops.EPI_STORE, ws.h3), "w3")
-            ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
-        else:
+            if h_stashed:
+                self._xa_only(s1, ws.xm2, "w1")
+                self._xa_only(s3, ws.xm2, "w3")
+            else:
+                self._linear_fwd_xa(s1, ws.xm2, ops.epi(ops.EPI_STORE, ws.h1), "w1")
+                self._linear_fwd_xa(s3, ws.xm2, ops.epi(ops.EPI_STORE, ws.h3), "w3")
+            if need_w2:
+                ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
+        elif not h_stashed:
             ops.lora_linear_fwd(ws.xm2, s1.W, ops.epi(ops.EPI_SWIGLU, ws.h, d2=ws.h1, d3=ws.h3), W_hi=s3.W)
-        self._linear_fwd_xa(s2, ws.h, ops.epi(ops.EPI_GATE_RESID, x_out, resid=ws.x2, gate=gate_mlp, tokens_per_frame=tpf,
-                                              d2=ws.branch_m if keep_branch else None), "w2")
-        if ex is not None and ex.hidden[b] is not None:
-            x_out.add_(ex.hidden[b].to(BF16)[None, :])
+        elif need_w2:
+            ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
+        if need_w2:
+            self._linear_fwd_xa(s2, ws.h, ops.epi(ops.EPI_GATE_RESID, x_out, resid=ws.x2, gate=gate_mlp, tokens_per_frame=tpf,
+                                                  d2=ws.branch_m if keep_branch else None), "w2")
+            if ex is not None and ex.hidden[b] is not None:
+                x_out.add_(ex.hidden[b].to(BF16)[None, :])
         self._ws_holds = b
         if getattr(self, "debug", None) is not None:
             for nm in ("mod", "xm1", "qkv", "qk", "o", "x1", "xn", "qc", "qcn", "kvc", "kcn", "oc", "x2", "xm2", "h1", "h3", "h", "y"):
@@ -470,7 +555,7 @@ class TTAEngine:
     # ------------------------------------------------------------------ block backward (dx in ws.dx, in place)
     def _block_bwd(self, b: int, x_in, ex: Optional[Extras]):
         ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
-        ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
+        self._bind(b)
         blk, st = self.dit.blocks[b], self.sites[b]
         N, Nc, Nn, M, tpf = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf
         mod = ws.mod
@@ -587,10 +672,15 @@ class TTAEngine:
             self.ws.branch_a = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
             self.ws.branch_m = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
 
-    def forward_tokens(self, text_valid: torch.Tensor, ex: Optional[Extras] = None) -> torch.Tensor:
+    def forward_tokens(self, text_valid: torch.Tensor, ex: Optional[Extras] = None, stash: bool = False) -> torch.Tensor:
         """ws.P / ws.timestep must hold the patchified input and the per-frame timestep.  Returns ws.pred [N,64] f32
-        (final-layer token layout) and leaves the block inputs in ws.xs for the backward."""
+        (final-layer token layout) and leaves the block inputs in ws.xs for the backward.  ``stash``: a backward
+        follows -- keep per-block activations in spare HBM (see _ensure_stash)."""
         ws, geo, C = self.ws, self.geo, self.C
+        self._stash_on = False
+        if stash:
+            self._ensure_stash(geo)
+            self._stash_on = True
         pe = self.dit.x_embedder.proj
         ops.gemm(geo.N, C, [(ws.P, pe.weight.view(C, 64), 64, False, None)], ops.epi(ops.EPI_STORE, ws.xs[0], bias=pe.bias))
         self._embed_time()
@@ -644,6 +734,7 @@ class TTAEngine:
                 self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
             self._block_bwd(b, ws.xs[b], ex)
         self._ws_holds = None
+        self._stash_on = False
 
     # ------------------------------------------------------------------ step-level helpers
     def set_inputs(self, cond, target, noise, sigma):
@@ -678,7 +769,7 @@ class _DiTFunction(torch.autograd.Function):
         ws = eng.ws
         ops.noise_patchify(ws.P, None, None, hidden_states[0].to(BF16).contiguous(), None, None, None)
         ws.timestep.copy_(timestep.reshape(-1).to(BF16).float())  # the DiT re-casts the timestep to its dtype first
-        eng.forward_tokens(text_valid, ex)
+        eng.forward_tokens(text_valid, ex, stash=any(getattr(ctx, "needs_input_grad", ())))
         out = torch.empty(1, 16, geo.T, geo.Hl, geo.Wl, dtype=F32, device=eng.device)
         ops.unpatchify(out[0], ws.pred, geo.T, geo.Hl, geo.Wl)
         ctx.dit, ctx.geo, ctx.adapter, ctx.ex = dit, geo, adapter, ex

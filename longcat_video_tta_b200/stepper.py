@@ -109,7 +109,7 @@ class TTAStepper:
         ex = self.extras = self.adapter.build_extras() if self.adapter is not None else None
         eng._prepare(geo, ex)
         eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
-        eng.forward_tokens(text_valid, ex)
+        eng.forward_tokens(text_valid, ex, stash=True)
         loss = eng.loss_and_dpred(True)
         only_bias = ex is not None and ex.out_bias is not None and not self._needs_dit_backward()
         eng.backward_tokens(ex, only_out_bias=only_bias)

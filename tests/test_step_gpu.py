@@ -297,3 +297,47 @@ def test_unconditioned_loss_variant(setup):
     rel = ((got - want).norm() / want.norm()).item()
     print(f"unconditioned forward rel-L2 {rel:.4g}")
     assert rel < 1e-2
+
+
+@pytest.mark.parametrize("target_ffn", [False, True])
+def test_activation_stash_matches_full_recompute(setup, monkeypatch, target_ffn):
+    """The spare-HBM activation stash (engine._ensure_stash) only replaces recomputation by stored copies of the same
+    values: adapter gradients with the stash off, partial (some blocks) and full must agree to run-to-run noise (the
+    attention backward sums its sub-block contributions in a timing-dependent order, so not bit for bit)."""
+    from longcat_video_tta_b200 import lora
+    from longcat_video_tta_b200.stepper import TTAStepper
+    s = setup
+    (sigma, eps), = replay_draws(s["train"], 1)
+    cond, train, prompt = (s[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    mask, sigma, eps = s["mask"].cuda(), sigma.cuda(), eps.to(BF16).cuda()
+    results = {}
+    for label, cap in (("off", "0"), ("partial", None), ("full", "4")):
+        dit = s["B200DiT"].from_oracle(s["oracle"])
+        torch.manual_seed(5)
+        mods = lora.inject_lora_into_dit(dit, rank=8, alpha=16.0, target_modules=["qkv", "proj"], target_ffn=target_ffn)
+        gen = torch.Generator().manual_seed(9)
+        with torch.no_grad():
+            for m in mods:
+                m.lora_up.weight.copy_((torch.randn(m.lora_up.weight.shape, generator=gen) * 0.02).to(BF16).cuda())
+        st = TTAStepper(dit)
+        eng = dit.engine
+        if cap is None:
+            # a cap that holds x1/x2 everywhere, qkv for some blocks and h1/h3 for none
+            geo = st._geometry(cond, train, eng.pack_text(prompt, mask))
+            per_x = geo.N * eng.C * 2
+            cap = str((2 * eng.L * per_x + (eng.L // 2) * 3 * per_x + per_x) / float(1 << 30))
+        monkeypatch.setenv("B200TTA_STASH_GB", cap)
+        loss = st.forward_backward(cond, train, prompt, mask, sigma, eps).item()
+        stash = eng._stash
+        counts = {k: stash[k] for k in ("k_x1", "k_x2", "k_qkv", "k_h")}
+        results[label] = (loss, [g.clone() for site in eng.lora_sites() for g in site.param_grads()], counts)
+    assert results["off"][2] == dict(k_x1=0, k_x2=0, k_qkv=0, k_h=0)
+    L = len(s["B200DiT"].from_oracle(s["oracle"]).blocks)
+    assert results["full"][2] == dict(k_x1=L, k_x2=L, k_qkv=L, k_h=L)
+    part = results["partial"][2]
+    assert part["k_x1"] == L and part["k_x2"] == L and 0 < part["k_qkv"] < L and part["k_h"] == 0
+    for label in ("partial", "full"):
+        assert abs(results[label][0] - results["off"][0]) <= 1e-6 * abs(results["off"][0])
+        worst = max(((a - b).norm() / (b.norm() + 1e-30)).item() for a, b in zip(results[label][1], results["off"][1]))
+        print(f"stash={label}: worst per-tensor relative L2 difference to full recompute {worst:.3g}")
+        assert worst < 1e-3, f"stash={label}: gradient differs from the full recompute"
