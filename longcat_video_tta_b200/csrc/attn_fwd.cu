@@ -147,8 +147,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
             issue_s(0, 0);
-            issue_s(1, 0);
-            umma_commit_e(&k_empty[0]);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_blocks; ++j) {
@@ -157,6 +155,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                 if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1u; }
                 mbar_wait(&v_full[stage], phase);
                 for (int t = 0; t < TILES; ++t) {
+                    if (j == 0 && t == 1) {
+                        // tile 1 starts one softmax later than tile 0: the two softmax groups then run in anti-phase
+                        // (one uses the MUFU while the other tile's MMAs run) instead of contending in phase
+                        issue_s(1, 0);
+                        umma_commit_e(&k_empty[0]);
+                    }
                     mbar_wait(&p_full[t], j & 1);
                     tc_fence_after();
                     issue_pv(t, stage, j > 0);
