@@ -6,7 +6,9 @@
 //                    S = Q K^T, dP = dO V^T (TS, N=64) -> dS = P o (dP - delta) (bf16 over dP in TMEM) -> dQ += dS K (TS)
 //   dkv_kernel   : one CTA per (128-row K/V block, head); K, V resident in shared memory; Q/dO stream through in 64-row
 //                  sub-tiles together with their LSE / delta values (staged by the producer warp):
-//                    S^T = K Q^T, dP^T = V dO^T (SS, N=64) -> P^T, dS^T (bf16 in TMEM) -> dV += P^T dO, dK += dS^T Q (TS)
+//                    S^T = K Q^T, dP^T = V dO^T (SS, N=64) -> P^T, dS^T (bf16 in TMEM) -> dV += P^T dO, dK += dS^T Q (TS);
+//                  S^T and dP^T are signalled separately (the exponentials overlap the dP^T MMAs) and dV is issued
+//                  as soon as P^T is stored, before dS^T exists
 // Why the A operands sit in TMEM where they fit: an SS-form tcgen05.mma re-reads its 128 x 16 A slice (4 KB) and its
 // N x 16 B slice from shared memory for every instruction, and shared memory delivers 128 B/clk -- measured
 // (scratch/mma_rate.cu): SS N=64 costs 48 clk, N=32 40 clk, while the TS form (A in TMEM) runs at the tensor rate N/2.
@@ -390,12 +392,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
     uint64_t* do_full = q_empty + STAGES;
     uint64_t* do_empty = do_full + STAGES;
     uint64_t* stat_full = do_empty + STAGES;
-    uint64_t* sdp_full = stat_full + STAGES;  // [2]
-    uint64_t* pds_full = sdp_full + 2;        // [2]
-    uint64_t* dkv_done = pds_full + 2;
+    uint64_t* s_full = stat_full + STAGES;    // [2] tcgen05.commit: S^T_b complete
+    uint64_t* dp_full = s_full + 2;           // [2] tcgen05.commit: dP^T_b complete
+    uint64_t* p_full = dp_full + 2;           // [2] compute group: P^T written over S^T_b
+    uint64_t* ds_full = p_full + 2;           // [2] compute group: dS^T written over dP^T_b
+    uint64_t* dkv_done = ds_full + 2;
     uint64_t* acc_zero = dkv_done + 1;
-    uint64_t* turn = acc_zero + 1;            // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(turn + 2);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_zero + 1);
     float* stat_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [STAGES][2][SUB]: LSE (log2), delta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -408,11 +411,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1);
             mbar_init(&stat_full[i], 1);
         }
-        for (int b = 0; b < 2; ++b) { mbar_init(&sdp_full[b], 1); mbar_init(&pds_full[b], GROUP_THREADS); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&s_full[b], 1); mbar_init(&dp_full[b], 1);
+            mbar_init(&p_full[b], GROUP_THREADS); mbar_init(&ds_full[b], GROUP_THREADS);
+        }
         mbar_init(dkv_done, 2);
         mbar_init(acc_zero, 2 * GROUP_THREADS);
-        mbar_init(&turn[0], 1); mbar_init(&turn[1], 1);
-        mbar_arrive(&turn[0]);   // issuer 0 has the first turn
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             dl.x = qc < q_lim ? __ldg(dl_g + qc) : 0.f;
             dl.y = qc + 1 < q_lim ? __ldg(dl_g + qc + 1) : 0.f;
             // do_empty[st] / q_empty[st] complete after the MMAs of sub-tile u - STAGES, which were issued after every
-            // compute thread arrived on pds_full, i.e. after the last read of this slot's statistics
+            // compute thread arrived on ds_full, i.e. after the last read of this slot's statistics
             mbar_wait(&do_empty[st], ph ^ 1u);
             mbar_wait(&q_empty[st], ph ^ 1u);
             if (lane == 0) {
@@ -484,29 +488,43 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
         mbar_wait(acc_zero, 0);
         tc_fence_after();
         const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s);
-        // strict turns between the two issuers, all waits before the turn is taken (see dq_kernel)
+        // Per own sub-tile u: dV(u) as soon as P^T(u) is there, then S^T(u+2) (re-uses the S^T buffer: ordered behind
+        // dV(u)), then dK(u) once dS^T(u) is there, then dP^T(u+2).  S^T and dP^T are signalled separately so the
+        // exponentials of a sub-tile overlap its own dP^T MMAs.
         long long w_ds = 0, w_tot0 = DBG_CLK();
-        for (int k = w; k < n_sub + 2; k += 2) {
-            const int u = k - 2, un = k;
-            const int st_n = un % STAGES, st_u = (u + STAGES) % STAGES;
-            if (un < n_sub) mbar_wait2(&q_full[st_n], (un / STAGES) & 1, &do_full[st_n], (un / STAGES) & 1);
+        if (w < n_sub) {
+            mbar_wait2(&q_full[w], 0, &do_full[w], 0);
+            tc_fence_after();
+            mma_ss_n64(tmem_base + w * 128, ka, smem_u32(q_s + w * SUBT_BYTES));
+            umma_commit_e(&s_full[w]);
+            mma_ss_n64(tmem_base + w * 128 + 64, va, smem_u32(do_s + w * SUBT_BYTES));
+            umma_commit_e(&dp_full[w]);
+        }
+        for (int u = w; u < n_sub; u += 2) {
+            const int st = u % STAGES, un = u + 2, st_n = un % STAGES;
+            const uint32_t j = (uint32_t)(u >> 1), ph_n = (un / STAGES) & 1;
             long long c0 = DBG_CLK();
-            if (u >= 0) mbar_wait2(&pds_full[w], (u >> 1) & 1, &turn[w], (k >> 1) & 1);
-            else mbar_wait(&turn[w], (k >> 1) & 1);
+            if (un < n_sub) mbar_wait2(&p_full[w], j & 1, &q_full[st_n], ph_n);
+            else mbar_wait(&p_full[w], j & 1);
             w_ds += DBG_CLK() - c0;
             tc_fence_after();
-            if (u >= 0) {
-                mma_ts_k64(t_dv, tmem_base + w * 128, smem_u32(do_s + st_u * SUBT_BYTES));
-                umma_commit_e(&do_empty[st_u]);
-                mma_ts_k64(t_dk, tmem_base + w * 128 + 64, smem_u32(q_s + st_u * SUBT_BYTES));
-                umma_commit_e(&q_empty[st_u]);
-            }
+            mma_ts_k64(t_dv, tmem_base + w * 128, smem_u32(do_s + st * SUBT_BYTES));
+            umma_commit_e(&do_empty[st]);
             if (un < n_sub) {
                 mma_ss_n64(tmem_base + w * 128, ka, smem_u32(q_s + st_n * SUBT_BYTES));
-                mma_ss_n64(tmem_base + w * 128 + 64, va, smem_u32(do_s + st_n * SUBT_BYTES));
-                umma_commit_e(&sdp_full[w]);
+                umma_commit_e(&s_full[w]);
             }
-            if (elect_one()) mbar_arrive(&turn[1 - w]);
+            c0 = DBG_CLK();
+            if (un < n_sub) mbar_wait2(&ds_full[w], j & 1, &do_full[st_n], ph_n);
+            else mbar_wait(&ds_full[w], j & 1);
+            w_ds += DBG_CLK() - c0;
+            tc_fence_after();
+            mma_ts_k64(t_dk, tmem_base + w * 128 + 64, smem_u32(q_s + st * SUBT_BYTES));
+            umma_commit_e(&q_empty[st]);
+            if (un < n_sub) {
+                mma_ss_n64(tmem_base + w * 128 + 64, va, smem_u32(do_s + st_n * SUBT_BYTES));
+                umma_commit_e(&dp_full[w]);
+            }
         }
         umma_commit_e(dkv_done);
         if (DBG_ON && warp == 1 && lane == 0) { DBG_SET(16, DBG_CLK() - w_tot0); DBG_SET(17, w_ds); DBG_SET(18, (n_sub + 1) / 2); }
@@ -540,42 +558,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             const float* dl_s = lse_s + SUB;
             mbar_wait(&stat_full[st], (u / STAGES) & 1);
             long long c1 = DBG_CLK(); w_pre += c1 - c0;
-            mbar_wait(&sdp_full[g], (u >> 1) & 1);
+            mbar_wait(&s_full[g], (u >> 1) & 1);
             tc_fence_after();
             long long c2 = DBG_CLK(); w_sdp += c2 - c1;
-            // two passes of 16 columns keep the live set under the 96-register budget of an 18-warp CTA; pass 1 stores
-            // over columns [8, 16), which pass 0 already consumed
+            // two passes of 16 columns keep the live set small; a pass stores its bf16 P^T over S^T columns this thread
+            // has already consumed.  The 32 probabilities stay in registers for dS^T.
+            float pf[32];
 #pragma unroll
             for (int hp = 0; hp < 2; ++hp) {
-                uint32_t sv[16], dp[16], pk[8], dk[8];
+                uint32_t sv[16], pk[8];
                 tmem_ld_32x32b_x16(t_s + hp * 16, sv);
-                tmem_ld_32x32b_x16(t_dp + hp * 16, dp);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    // the per-column statistics are warp-uniform broadcast reads: 16-byte loads halve the number of
-                    // shared-memory wavefronts that compete with the MMA operand fetches (ncu: LSU traffic was ~40 %
-                    // of the shared-memory cycles of this kernel)
+                    // per-column statistics are warp-uniform broadcast reads: 16-byte loads keep the LSU off the
+                    // shared-memory banks the MMA operand fetches need
                     const float4 l4 = *reinterpret_cast<const float4*>(lse_s + hp * 16 + i);
-                    const float4 d4 = *reinterpret_cast<const float4*>(dl_s + hp * 16 + i);
                     float a0 = fmaf(__uint_as_float(sv[i]), p.scale_log2, -l4.x);
                     float a1 = fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -l4.y);
                     float a2 = fmaf(__uint_as_float(sv[i + 2]), p.scale_log2, -l4.z);
                     float a3 = fmaf(__uint_as_float(sv[i + 3]), p.scale_log2, -l4.w);
                     if (!all_rows) { a0 += row_bias; a1 += row_bias; a2 += row_bias; a3 += row_bias; }
                     const float p0 = fast_exp2(a0), p1 = fast_exp2(a1), p2 = fast_exp2(a2), p3 = fast_exp2(a3);
+                    pf[hp * 16 + i] = p0; pf[hp * 16 + i + 1] = p1; pf[hp * 16 + i + 2] = p2; pf[hp * 16 + i + 3] = p3;
                     pk[i >> 1] = pack_bf16x2(p0, p1);
                     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-                    dk[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dp[i]) - d4.x), p1 * (__uint_as_float(dp[i + 1]) - d4.y));
-                    dk[(i >> 1) + 1] = pack_bf16x2(p2 * (__uint_as_float(dp[i + 2]) - d4.z), p3 * (__uint_as_float(dp[i + 3]) - d4.w));
                 }
-                tmem_st_32x32b_x8(t_s + hp * 8, pk);     // P^T  (bf16) over S^T columns this thread already loaded
-                tmem_st_32x32b_x8(t_dp + hp * 8, dk);    // dS^T (bf16) likewise over dP^T
+                tmem_st_32x32b_x8(t_s + hp * 8, pk);     // P^T (bf16)
             }
-            long long c3 = DBG_CLK(); w_math += c3 - c2;
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&pds_full[g]);
+            mbar_arrive(&p_full[g]);                     // dV(u) can go while dS^T is still being computed
+            long long c3 = DBG_CLK(); w_math += c3 - c2;
+            mbar_wait(&dp_full[g], (u >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+                uint32_t dp[16], dk[8];
+                tmem_ld_32x32b_x16(t_dp + hp * 16, dp);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(dl_s + hp * 16 + i);
+                    dk[i >> 1] = pack_bf16x2(pf[hp * 16 + i] * (__uint_as_float(dp[i]) - d4.x),
+                                             pf[hp * 16 + i + 1] * (__uint_as_float(dp[i + 1]) - d4.y));
+                    dk[(i >> 1) + 1] = pack_bf16x2(pf[hp * 16 + i + 2] * (__uint_as_float(dp[i + 2]) - d4.z),
+                                                   pf[hp * 16 + i + 3] * (__uint_as_float(dp[i + 3]) - d4.w));
+                }
+                tmem_st_32x32b_x8(t_dp + hp * 8, dk);    // dS^T (bf16) over dP^T columns this thread already loaded
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&ds_full[g]);
             w_st += DBG_CLK() - c3;
         });
         if (DBG_ON && warp == 3 && lane == 0) {
