@@ -22,6 +22,19 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
     t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
 }
+// same as unpack8, but opaque to common-subexpression elimination: a kernel that keeps a row PACKED in registers and
+// unpacks it once per pass must not have the unpacked copy kept live across passes (that doubles the register need)
+__device__ __forceinline__ void unpack8_opaque(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t lo, hi;
+        asm volatile("shl.b32 %0, %1, 16;" : "=r"(lo) : "r"(w[i]));
+        asm volatile("and.b32 %0, %1, 0xffff0000;" : "=r"(hi) : "r"(w[i]));
+        f[2 * i] = __uint_as_float(lo);
+        f[2 * i + 1] = __uint_as_float(hi);
+    }
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     uint4 u;
     u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -41,7 +54,7 @@ __device__ __forceinline__ void load_param8(const void* base, long long idx, int
 
 // ------------------------------------------------------------------------------------ LayerNorm + modulate
 template <int CH>  // C = CH * 256
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ln_mod_fwd_kernel(
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2) ln_mod_fwd_kernel(
     __nv_bfloat16* __restrict__ Y, long long ldy, const __nv_bfloat16* __restrict__ X, long long ldx,
     const void* __restrict__ scale, const void* __restrict__ shift, long long mod_ld, int params_bf16, float mul_base,
     long long rows, int tpf, float eps) {
@@ -49,31 +62,42 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) ln_mod_fwd_kernel(
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     constexpr int C = CH * 256;
-    float v[CH][8];
+    // the row stays PACKED (bf16) in registers and is unpacked in each of the three passes: 64 instead of 128 data
+    // registers at C = 4096 (the fp32 version needed 255 registers = one 8-warp block per SM, ~45 % of HBM bandwidth)
+    uint4 raw[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) raw[c] = __ldg(reinterpret_cast<const uint4*>(X + row * ldx + (c * 32 + lane) * 8));
     float s = 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(X + row * ldx + (c * 32 + lane) * 8)), v[c]);
+        float v[8];
+        unpack8_opaque(raw[c], v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[c][i];
+        for (int i = 0; i < 8; ++i) s += v[i];
     }
     const float mean = warp_sum(s) * (1.0f / C);
     float q = 0.f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c)
+    for (int c = 0; c < CH; ++c) {
+        float v[8];
+        unpack8_opaque(raw[c], v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { v[c][i] -= mean; q += v[c][i] * v[c][i]; }
+        for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q += d * d; }
+    }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
     const long long f = row / tpf;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-        float sc[8], sh[8];
+        float sc[8], sh[8], v[8];
         const long long idx = f * mod_ld + (c * 32 + lane) * 8;
         load_param8(scale, idx, params_bf16, sc);
         load_param8(shift, idx, params_bf16, sh);
+        unpack8_opaque(raw[c], v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[c][i] = fmaf(v[c][i] * rstd, mul_base + sc[i], sh[i]);
-        *reinterpret_cast<uint4*>(Y + row * ldy + (c * 32 + lane) * 8) = pack8(v[c]);
+        for (int i = 0; i < 8; ++i) v[i] = fmaf((v[i] - mean) * rstd, mul_base + sc[i], sh[i]);
+        *reinterpret_cast<uint4*>(Y + row * ldy + (c * 32 + lane) * 8) = pack8(v);
+        // keep ptxas from hoisting all 2 x CH parameter loads (256 live floats at C = 4096) above the first store
+        if ((c & 3) == 3) asm volatile("" ::: "memory");
     }
 }
 
