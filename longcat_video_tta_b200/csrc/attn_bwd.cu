@@ -30,6 +30,7 @@
 #include "host_common.h"
 #include "ptx.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 #ifndef B200TTA_ATTN_DEBUG
 #define B200TTA_ATTN_DEBUG 0
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
         // invalid rows (beyond the segment) get lse = +inf so that exp2(s - lse) = 0 without a per-element select
         const float neg_lse = row_ok ? -lse2 : -INFINITY;
         // this thread's 64 bytes of dS row `row`: 16-byte chunks 4 half .. 4 half + 3, XOR-swizzled with (row & 7)
-        uint8_t* ds_row = ds_s + g * DS_BYTES + row * 128;
+        const uint32_t ds_row = smem_u32(ds_s + g * DS_BYTES + row * 128);
         const int sw = row & 7;
         long long w_sdp = 0, w_ld = 0, w_math = 0, w_st = 0, c_all0 = DBG_CLK();
         for (int u = g; u < n_sub; u += 2) {
@@ -356,8 +357,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             mbar_wait(&ds_free[g], (j & 1) ^ 1u);   // dQ MMA of sub-block u - 2 has read the tile (first pass: fresh barrier)
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(ds_row + (((half * 4 + c) ^ sw) << 4)) =
-                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                sts_b32x4(ds_row + (((half * 4 + c) ^ sw) << 4), pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
             fence_proxy_async();
             mbar_arrive(&ds_full[g]);
             w_st += DBG_CLK() - c3;
@@ -551,11 +551,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             if ((u & 1) != g) return;
             const int st = u % STAGES;
             long long c0 = DBG_CLK();
-            const bool row_ok = kv_row < p.seg_kv_len[s];
-            const float row_bias = row_ok ? 0.f : -INFINITY;   // rows beyond the segment's kv_len contribute nothing
-            const bool all_rows = kv0 + BT <= p.seg_kv_len[s]; // block-uniform: the common case needs no row handling
-            const float* lse_s = stat_s + st * 2 * SUB + half * 32;
-            const float* dl_s = lse_s + SUB;
+            // rows beyond the segment's kv_len contribute nothing.  Block-uniform: only the K/V block that straddles the
+            // end of a segment takes the masked variant; folded into one loop ptxas predicates an extra add per element.
+            const bool all_rows = kv0 + BT <= p.seg_kv_len[s];
+            const float row_bias = kv_row < p.seg_kv_len[s] ? 0.f : -INFINITY;
+            const uint32_t lse_a = smem_u32(stat_s + st * 2 * SUB + half * 32), dl_a = lse_a + SUB * 4;
             mbar_wait(&stat_full[st], (u / STAGES) & 1);
             long long c1 = DBG_CLK(); w_pre += c1 - c0;
             mbar_wait(&s_full[g], (u >> 1) & 1);
@@ -564,28 +564,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             // two passes of 16 columns keep the live set small; a pass stores its bf16 P^T over S^T columns this thread
             // has already consumed.  The 32 probabilities stay in registers for dS^T.
             float pf[32];
+            auto exp_pass = [&](auto masked_tag) {
+                constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
-            for (int hp = 0; hp < 2; ++hp) {
-                uint32_t sv[16], pk[8];
-                tmem_ld_32x32b_x16(t_s + hp * 16, sv);
-                tmem_ld_wait();
+                for (int hp = 0; hp < 2; ++hp) {
+                    uint32_t sv[16], pk[8];
+                    tmem_ld_32x32b_x16(t_s + hp * 16, sv);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    // per-column statistics are warp-uniform broadcast reads: 16-byte loads keep the LSU off the
-                    // shared-memory banks the MMA operand fetches need
-                    const float4 l4 = *reinterpret_cast<const float4*>(lse_s + hp * 16 + i);
-                    float a0 = fmaf(__uint_as_float(sv[i]), p.scale_log2, -l4.x);
-                    float a1 = fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -l4.y);
-                    float a2 = fmaf(__uint_as_float(sv[i + 2]), p.scale_log2, -l4.z);
-                    float a3 = fmaf(__uint_as_float(sv[i + 3]), p.scale_log2, -l4.w);
-                    if (!all_rows) { a0 += row_bias; a1 += row_bias; a2 += row_bias; a3 += row_bias; }
-                    const float p0 = fast_exp2(a0), p1 = fast_exp2(a1), p2 = fast_exp2(a2), p3 = fast_exp2(a3);
-                    pf[hp * 16 + i] = p0; pf[hp * 16 + i + 1] = p1; pf[hp * 16 + i + 2] = p2; pf[hp * 16 + i + 3] = p3;
-                    pk[i >> 1] = pack_bf16x2(p0, p1);
-                    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+                    for (int i = 0; i < 16; i += 4) {
+                        // per-column statistics are warp-uniform broadcast reads: 16-byte loads keep the LSU off the
+                        // shared-memory banks the MMA operand fetches need
+                        const float4 l4 = lds_f32x4(lse_a + (hp * 16 + i) * 4);
+                        float a0 = fmaf(__uint_as_float(sv[i]), p.scale_log2, -l4.x);
+                        float a1 = fmaf(__uint_as_float(sv[i + 1]), p.scale_log2, -l4.y);
+                        float a2 = fmaf(__uint_as_float(sv[i + 2]), p.scale_log2, -l4.z);
+                        float a3 = fmaf(__uint_as_float(sv[i + 3]), p.scale_log2, -l4.w);
+                        if (MASKED) { a0 += row_bias; a1 += row_bias; a2 += row_bias; a3 += row_bias; }
+                        const float p0 = fast_exp2(a0), p1 = fast_exp2(a1), p2 = fast_exp2(a2), p3 = fast_exp2(a3);
+                        pf[hp * 16 + i] = p0; pf[hp * 16 + i + 1] = p1; pf[hp * 16 + i + 2] = p2; pf[hp * 16 + i + 3] = p3;
+                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                        pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+                    }
+                    tmem_st_32x32b_x8(t_s + hp * 8, pk);     // P^T (bf16)
                 }
-                tmem_st_32x32b_x8(t_s + hp * 8, pk);     // P^T (bf16)
-            }
+            };
+            if (all_rows) exp_pass(std::false_type{}); else exp_pass(std::true_type{});
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[g]);                     // dV(u) can go while dS^T is still being computed
@@ -599,7 +603,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                    const float4 d4 = *reinterpret_cast<const float4*>(dl_s + hp * 16 + i);
+                    const float4 d4 = lds_f32x4(dl_a + (hp * 16 + i) * 4);
                     dk[i >> 1] = pack_bf16x2(pf[hp * 16 + i] * (__uint_as_float(dp[i]) - d4.x),
                                              pf[hp * 16 + i + 1] * (__uint_as_float(dp[i + 1]) - d4.y));
                     dk[(i >> 1) + 1] = pack_bf16x2(pf[hp * 16 + i + 2] * (__uint_as_float(dp[i + 2]) - d4.z),

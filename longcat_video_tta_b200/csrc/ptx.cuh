@@ -27,6 +27,17 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// Explicit shared-space accesses: a pointer computed from the aligned dynamic-smem base through uintptr_t loses its
+// address space and ptxas falls back to generic LD.E / ST.E (seen in the attention kernels' SASS).
+__device__ __forceinline__ float4 lds_f32x4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_b32x4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
