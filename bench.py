@@ -260,7 +260,7 @@ def run_b200(args):
         d = prof[fam]
         ach = d["flops"] / (d["ms"] / 1000.0) / 1e12
         roof = {"kernel": fam, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                "frac": ach / peaks["tflops_sustained"], "traffic": _ncu_traffic(fam),
                 "peak_source": peaks["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "launches_per_step": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                 "algorithmic_tflop_per_launch": d["flops"] / d["n"] / 1e12, "share_of_step": d["ms"] / tot_ms}
@@ -327,6 +327,28 @@ def _family(name, a):
     if fam == "lora_linear_bwd":
         return "linear_bwd (tcgen05 GEMM dX + LoRA grads)"
     return fam
+
+
+def _ncu_traffic(family):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel family from the
+    committed `ncu --set full` capture (profiles/r1_ncu_attention_full.json, headline shape); None if not captured.
+    attn_bwd[self] = dq_kernel + dkv_kernel (the delta pre-pass, 0.6 GB algorithmic, was not captured)."""
+    kernels = {"attn_bwd[self]": ("dq_kernel", "dkv_kernel"), "attn_fwd[self]": ("attn_fwd",)}.get(family)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_attention_full.json")
+    if kernels is None or not os.path.exists(path):
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        with open(path) as f:
+            cap = json.load(f)
+        total = 0.0
+        for k in kernels:
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                val, u = cap[k][m].split()
+                total += float(val) * unit[u]
+        return total
+    except (KeyError, ValueError):
+        return None
 
 
 def _stash_summary(eng):
