@@ -416,3 +416,91 @@ def test_attn_bwd_cross_attention_shape(ops):
     close(dq, qf.grad)
     close(dkv[:, 0], kf.grad)
     close(dkv[:, 1], vf.grad)
+
+
+# ---------------------------------------------------------------------------------------------- headline sizes
+# BASELINE.json configs[1]: N = 37 440 tokens (6 240 context + 31 200 noised), 32 heads x 128.  A dense fp32 reference of
+# the whole problem does not fit, so these tests use size-independent properties plus fp32 spot checks on slices.
+HEAD_N, HEAD_NC, HEAD_H, HEAD_D = 37440, 6240, 32, 128
+HEAD_SEGS = [(0, HEAD_NC, HEAD_NC), (HEAD_NC, HEAD_N, HEAD_N)]
+
+
+@pytest.fixture(scope="module")
+def headline_attention(ops):
+    qkv = rnd(HEAD_N, 3, HEAD_H, HEAD_D, seed=11)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    o = torch.zeros(HEAD_N, HEAD_H, HEAD_D, dtype=BF16, device="cuda")
+    lse = torch.zeros(HEAD_H, HEAD_N, dtype=F32, device="cuda")
+    ops.attn_fwd(q, k, v, o, lse, HEAD_SEGS, HEAD_D ** -0.5)
+    return q, k, v, o, lse
+
+
+def test_attn_fwd_headline_size_properties_and_slices(ops, headline_attention):
+    q, k, v, o, lse = headline_attention
+    scale = HEAD_D ** -0.5
+    # (1) softmax rows sum to one: with V = 1 the output is 1 whatever Q and K are
+    ones = torch.ones_like(v)
+    o1 = torch.empty_like(o)
+    lse1 = torch.empty_like(lse)
+    ops.attn_fwd(q, k, ones, o1, lse1, HEAD_SEGS, scale)
+    assert (o1.float() - 1.0).abs().max().item() <= 2 ** -7
+    assert torch.equal(lse1, lse)                      # the statistics do not depend on V
+    # (2) fp32 reference on slices: first / last rows of each segment, two heads
+    for (a, b, kv) in HEAD_SEGS:
+        for rows in (slice(a, a + 192), slice(b - 200, b)):
+            for h in (0, HEAD_H - 1):
+                s = (q[rows, h].float() @ k[:kv, h].float().t()) * scale
+                ref = torch.softmax(s, -1) @ v[:kv, h].float()
+                close(o[rows, h], ref)
+                close(lse[h, rows], torch.logsumexp(s, -1), rtol=1e-3, atol=1e-2)
+
+
+def test_attn_bwd_headline_size_properties_and_slices(ops, headline_attention):
+    q, k, v, o, lse = headline_attention
+    scale = HEAD_D ** -0.5
+    do = rnd(HEAD_N, HEAD_H, HEAD_D, seed=12)
+    dqkv = torch.full((HEAD_N, 3, HEAD_H, HEAD_D), float("nan"), dtype=BF16, device="cuda")
+    delta = torch.empty(HEAD_H, HEAD_N, dtype=F32, device="cuda")
+    ops.attn_bwd(dqkv[:, 0], dqkv[:, 1], dqkv[:, 2], do, o, lse, delta, q, k, v, HEAD_SEGS, scale)
+    dq, dk, dv = dqkv[:, 0], dqkv[:, 1], dqkv[:, 2]
+    assert torch.isfinite(dqkv.float()).all()
+    # (1) checksum: every row of P sums to one, so sum_kv dV[kv] = sum_q dO[q] per head (fp32 accumulation of bf16 P)
+    got, want = dv.float().sum(0), do.float().sum(0)
+    assert ((got - want).abs().max() / want.abs().max()).item() < 2e-2
+    # (2) linearity in dO (x2 is exact in bf16; only the summation order inside the kernels may differ run to run)
+    dqkv2 = torch.empty_like(dqkv)
+    ops.attn_bwd(dqkv2[:, 0], dqkv2[:, 1], dqkv2[:, 2], (do.float() * 2).to(BF16), o, lse, delta, q, k, v, HEAD_SEGS, scale)
+    for a, b in ((dqkv2[:, 0], dq), (dqkv2[:, 1], dk), (dqkv2[:, 2], dv)):
+        rel = ((a.float() - 2 * b.float()).norm() / (2 * b.float().norm())).item()
+        assert rel < 5e-3, rel
+    # (3) fp32 autograd on one head: dQ on row slices of both segments, dK / dV everywhere (needs every query)
+    h = 5
+    qf, kf, vf = (t[:, h].float().detach().requires_grad_(True) for t in (q, k, v))
+    out = torch.zeros(HEAD_N, HEAD_D, device="cuda")
+    chunks = []
+    for (a, b, kv) in HEAD_SEGS:
+        for r0 in range(a, b, 4096):                 # chunked over queries: a [4096, 37440] fp32 score block at a time
+            r1 = min(b, r0 + 4096)
+            s = (qf[r0:r1] @ kf[:kv].t()) * scale
+            chunks.append(((torch.softmax(s, -1) @ vf[:kv]) * do[r0:r1, h].float()).sum())
+    torch.stack(chunks).sum().backward()
+    close(dq[:, h], qf.grad)
+    close(dk[:, h], kf.grad)
+    close(dv[:, h], vf.grad)
+
+
+def test_gemm_headline_size_slices(ops):
+    """qkv projection of the headline step: [37440, 4096] x [12288, 4096]^T, checked on random rows against fp32."""
+    M, N, K = HEAD_N, 3 * 4096, 4096
+    a, w = rnd(M, K, seed=21), rnd(N, K, scale=0.02, seed=22)
+    bias = rnd(N, seed=23)
+    out = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(M, N, [(a, w, K, False, None)], ops.epi(ops.EPI_STORE, out, bias=bias))
+    rows = torch.randint(0, M, (256,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    rows = torch.cat([rows, torch.tensor([0, 127, 128, M - 129, M - 128, M - 1], device="cuda")])
+    ref = a[rows].float() @ w.float().t() + bias.float()
+    close(out[rows], ref)
+    # dX form (MN-major B, no transposed copy): [37440, 12288] x [12288, 4096]
+    dx = torch.empty(M, K, dtype=BF16, device="cuda")
+    ops.gemm(M, K, [(out, w, N, True, None)], ops.epi(ops.EPI_STORE, dx))
+    close(dx[rows], out[rows].float() @ w.float())
