@@ -214,3 +214,64 @@ def test_anchor_loss_matches_reference_golden(env, golden_dir):
                                                        device="cuda", dtype=BF16)
     print("anchor loss", loss, "golden", g["anchor_loss0"])
     assert abs(loss - g["anchor_loss0"]) <= 2e-2 * g["anchor_loss0"]
+
+
+# ---- known-answer tests that hold whatever the upstream DiT details are ---------------------------------
+@pytest.mark.parametrize("method", ["delta_a", "delta_b_timestep_g2", "delta_b_hidden_g2", "delta_c", "film_full_g2"])
+def test_zero_init_adapter_is_the_base_model(env, method):
+    """delta / FiLM trainables start at zero: the adapted forward must reproduce the base DiT bit for bit."""
+    from longcat_video_tta_b200.dit import B200DiT
+    from oracle import tta_oracle as T
+    (sigma, eps), = replay_draws(env["train"], 1)
+    cond, train, prompt = (env[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    mask, sigma, eps = env["mask"].cuda(), sigma.cuda(), eps.to(BF16).cuda()
+    base = B200DiT.from_oracle(env["oracle"])
+    w = mine_method(env["oracle"], method)
+    assert all(float(p.detach().abs().max()) == 0.0 for p in w.trainable())
+    with torch.no_grad():
+        l0 = T.fm_loss_given(base, cond, train, prompt, mask, sigma, eps, BF16)
+        l1 = T.fm_loss_given(w, cond, train, prompt, mask, sigma, eps, BF16)
+    assert torch.equal(l0, l1), (l0.item(), l1.item())
+
+
+def test_lr_1e_minus_20_is_a_no_op(env):
+    """the reference's own no-op control (delta_lr = 1e-20): parameters stay where they started."""
+    from longcat_video_tta_b200 import adapters as A
+    w = mine_method(env["oracle"], "delta_a")
+    cond, train, prompt = (env[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    torch.manual_seed(42)
+    out = A.optimize_delta_a(w, cond, train, prompt, env["mask"].cuda(), num_steps=3, lr=1e-20, device="cuda")
+    assert len(out["losses"]) == 3 and all(l == l for l in out["losses"])
+    assert out["delta_norm"] <= 1e-17 and float(w.delta.detach().abs().max()) <= 1e-18
+
+
+def test_custom_and_builtin_lora_agree_on_unfused_linears(env):
+    """LoRALinear and the builtin LoRAModule are the same arithmetic on a linear that is not a fused qkv / kv
+    (attn.proj, cross_attn.proj): same weights => same loss and the same gradients."""
+    from longcat_video_tta_b200 import lora
+    from longcat_video_tta_b200.dit import B200DiT
+    from longcat_video_tta_b200.stepper import TTAStepper
+    (sigma, eps), = replay_draws(env["train"], 1)
+    cond, train, prompt = (env[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    mask, sigma, eps = env["mask"].cuda(), sigma.cuda(), eps.to(BF16).cuda()
+    d1, d2 = B200DiT.from_oracle(env["oracle"]), B200DiT.from_oracle(env["oracle"])
+    torch.manual_seed(3)
+    custom = lora.inject_lora_into_dit(d1, rank=8, alpha=16.0, target_modules=["proj"])
+    builtin = lora.inject_builtin_lora_into_dit(d2, rank=8, alpha=16.0, target_modules=["proj"])
+    assert len(custom) == len(builtin) == 2 * len(d1.blocks)
+    gen = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        for c, b in zip(custom, builtin):
+            up = (torch.randn(c.lora_up.weight.shape, generator=gen) * 0.02).to(BF16).cuda()
+            c.lora_up.weight.copy_(up)
+            b.lora_up.weight.copy_(up)
+            b.lora_down.weight.copy_(c.lora_down.weight)
+    s1, s2 = TTAStepper(d1), TTAStepper(d2, build_optimizer=True)
+    l1 = s1.forward_backward(cond, train, prompt, mask, sigma, eps).item()
+    l2 = s2.forward_backward(cond, train, prompt, mask, sigma, eps).item()
+    assert abs(l1 - l2) <= 1e-6 * abs(l1)
+    g1 = [g for site in d1.engine.lora_sites() for g in site.param_grads()]
+    g2 = [g for site in d2.engine.lora_sites() for g in site.param_grads()]
+    assert len(g1) == len(g2) == 2 * len(custom)
+    for a, b in zip(g1, g2):
+        assert ((a.float() - b.float()).norm() / (a.float().norm() + 1e-30)).item() < 1e-3
