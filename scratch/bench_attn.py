@@ -46,13 +46,9 @@ if not hasattr(lib, "b200tta_debug_read"):
 lib.b200tta_debug_read.argtypes = [C.c_void_p]
 if lib.b200tta_debug_read(buf) == 0:
     d = list(buf)
-    n = max(d[2], 1)
-    print(f"dq CTA(0,0): issuer own-subs {d[2]}; issuer total {d[0]} clk ({d[0]/n:.0f}/own-sub), waiting ds_full {d[1]/n:.0f}, v_full {d[3]/n:.0f}, s_free+k {d[10]/n:.0f}")
-    m = n
-    print(f"  compute warp2: total {d[4]} ({d[4]/m:.0f}/own-sub): wait s_full {d[5]/m:.0f}, ld S+exp {d[8]/m:.0f}, wait dp_full+ld {d[6]/m:.0f}, ds+st {d[9]/m:.0f}")
     n = max(d[18], 1); m = n
-    print(f"dkv CTA(0,0): n_sub {d[18]}; MMA thread total {d[16]} clk ({d[16]/n:.0f}/sub), waiting pds_full {d[17]/n:.0f}/sub")
-    print(f"  compute warp2: total {d[20]} ({d[20]/m:.0f}/own-sub): wait sdp {d[21]/m:.0f}, pre {d[22]/m:.0f}, ld+bar+math {d[23]/m:.0f}, st+arrive {d[24]/m:.0f}")
+    print(f"dkv CTA(0,0): issuer own-subs {d[18]}; issuer total {d[16]} clk ({d[16]/n:.0f}/own-sub), waiting p/ds_full {d[17]/n:.0f}")
+    print(f"  compute warp 3: total {d[20]} ({d[20]/m:.0f}/own-sub): wait s_full {d[21]/m:.0f}, stats {d[22]/m:.0f}, exp+P^T {d[23]/m:.0f}, dP^T wait + dS^T {d[24]/m:.0f}")
 import os
 if not os.environ.get("B200TTA_DEBUG_NO_DQ") and not os.environ.get("B200TTA_DEBUG_NO_DKV"):
     for var in ("B200TTA_DEBUG_NO_DQ", "B200TTA_DEBUG_NO_DKV"):
