@@ -490,6 +490,9 @@ class TTAEngine:
         q = ws.qk.view(N, 2 * H, D)[:, :H]
         k = ws.qk.view(N, 2 * H, D)[:, H:]
         v = ws.qkv.view(N, 3 * H, D)[:, 2 * H:]
+        if getattr(self, "_ctx_fill", False):   # keep the context rows' K / V for the noise-rows-only forwards that follow
+            self._ctx["k"][b].view(Nc, H, D).copy_(k[:Nc])
+            self._ctx["v"][b].view(Nc, H, D).copy_(v[:Nc])
         if not recompute:
             ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
         s = st["proj"]
@@ -551,6 +554,86 @@ class TTAEngine:
                 self._tap(b, "f_" + nm, getattr(ws, nm))
             self._tap(b, "f_xin", x_in)
             self._tap(b, "f_xout", x_out)
+
+    # ------------------------------------------------------------------ forward with cached context K/V
+    # The context (clean conditioning) frames carry timestep 0 and only attend to themselves, so for a fixed video, text
+    # and adapter state their rows are the SAME in every forward whatever sigma / noise the other frames get.  The
+    # anchored early stopper evaluates sigmas x draws = 6 forwards on [cond | val] per check (early_stopping.py:293-317
+    # -> common.py:492-559): the first one stores every block's context K (normed + RoPE'd) and V, the other five run
+    # the noised rows only against [cached context K/V | their own K/V].  Same idea as upstream's use_kv_cache in
+    # generate_vc (common.py:598-611).  Forward only.
+    def _ensure_ctx_cache(self, geo: Geometry):
+        c = getattr(self, "_ctx", None)
+        if c is None or c["geo"] != geo:
+            self._ctx = None
+            e = lambda: torch.empty(self.L, geo.Nc, self.C, dtype=BF16, device=self.device)
+            try:
+                k, v = e(), e()
+            except torch.OutOfMemoryError:      # the training stash is an optimisation: give its memory back
+                self._release_stash()
+                torch.cuda.empty_cache()
+                k, v = e(), e()
+            self._ctx = c = {"geo": geo, "k": k, "v": v, "valid": False}
+        return c
+
+    def _block_fwd_noise_rows(self, b: int, x_in, x_out, ex: Optional[Extras]):
+        """_block_fwd restricted to the noised rows [Nc:], self-attention keys/values = cached context + own rows."""
+        ws, geo, C, H, D = self.ws, self.geo, self.C, self.H, self.D
+        self._bind(b)
+        blk, st, cache = self.dit.blocks[b], self.sites[b], self._ctx
+        N, Nc, Nn, M, tpf, Tc = geo.N, geo.Nc, geo.Nn, geo.M, geo.tpf, geo.n_cond
+        ada = blk.adaLN_modulation[1]
+        film = None
+        if ex is not None and ex.film[b] is not None:
+            film = ex.film[b].to(F32)[None, :].expand(geo.T, -1).contiguous()
+        ops.skinny_linear(ws.mod, self._t_for_block(b, ex), ada.weight, ada.bias, act=1, addend=film)
+        mod = ws.mod[Tc:]                                   # modulation rows of the noised frames
+        shift_msa, scale_msa, gate_msa = mod[:, 0:C], mod[:, C:2 * C], mod[:, 2 * C:3 * C]
+        shift_mlp, scale_mlp, gate_mlp = mod[:, 3 * C:4 * C], mod[:, 4 * C:5 * C], mod[:, 5 * C:6 * C]
+        xin = x_in[Nc:]
+        # ---- self attention: queries = noised rows, keys / values = all rows
+        ops.ln_mod_fwd(ws.xm1[Nc:], xin, scale_msa, shift_msa, tokens_per_frame=tpf)
+        s = st["qkv"]
+        self._linear_fwd_xa(s, ws.xm1[Nc:], ops.epi(ops.EPI_STORE, ws.qkv[Nc:], bias=s.bias), "qkv")
+        ops.qk_rmsnorm_rope_fwd(ws.qk[Nc:], ws.qkv[Nc:], blk.attn.q_norm.weight, blk.attn.k_norm.weight, H, H,
+                                grid_hw=(geo.gh, geo.gw), row_offset=Nc, rope_base=self.dit.config.rope_base)
+        q = ws.qk.view(N, 2 * H, D)[:, :H]
+        k = ws.qk.view(N, 2 * H, D)[:, H:]
+        v = ws.qkv.view(N, 3 * H, D)[:, 2 * H:]
+        k[:Nc].copy_(cache["k"][b].view(Nc, H, D))
+        v[:Nc].copy_(cache["v"][b].view(Nc, H, D))
+        ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, [(Nc, N, N)], self.softmax_scale)
+        s = st["proj"]
+        self._linear_fwd_xa(s, ws.o[Nc:], ops.epi(ops.EPI_GATE_RESID, ws.x1[Nc:], bias=s.bias, resid=xin, gate=gate_msa,
+                                                  tokens_per_frame=tpf), "proj")
+        # ---- cross attention (the noised rows are the only ones that ever had it)
+        nrm = blk.pre_crs_attn_norm
+        ops.ln_mod_fwd(ws.xn, ws.x1[Nc:], nrm.weight, nrm.bias, tokens_per_frame=tpf, affine=True)
+        s = st["q_linear"]
+        self._linear_fwd_xa(s, ws.xn, ops.epi(ops.EPI_STORE, ws.qc, bias=s.bias), "q_linear")
+        s = st["kv_linear"]
+        self._linear_fwd_xa(s, ws.y, ops.epi(ops.EPI_STORE, ws.kvc, bias=s.bias), "kv_linear")
+        ops.qk_rmsnorm_rope_fwd(ws.qcn, ws.qc, blk.cross_attn.q_norm.weight, None, H, 0, rope=False)
+        ops.qk_rmsnorm_rope_fwd(ws.kcn, ws.kvc[:, :C], blk.cross_attn.k_norm.weight, None, H, 0, rope=False)
+        vc = ws.kvc.view(M, 2 * H, D)[:, H:]
+        ops.attn_fwd(ws.qcn.view(Nn, H, D), ws.kcn.view(M, H, D), vc, ws.oc.view(Nn, H, D), ws.lsec,
+                     [(0, Nn, M)], self.softmax_scale)
+        s = st["cproj"]
+        self._linear_fwd_xa(s, ws.oc, ops.epi(ops.EPI_GATE_RESID, ws.x2[Nc:], bias=s.bias, resid=ws.x1[Nc:]), "cproj")
+        # ---- FFN
+        ops.ln_mod_fwd(ws.xm2[Nc:], ws.x2[Nc:], scale_mlp, shift_mlp, tokens_per_frame=tpf)
+        s1, s3, s2 = st["w1"], st["w3"], st["w2"]
+        if s1.has_lora or s3.has_lora:
+            self._linear_fwd_xa(s1, ws.xm2[Nc:], ops.epi(ops.EPI_STORE, ws.h1[Nc:]), "w1")
+            self._linear_fwd_xa(s3, ws.xm2[Nc:], ops.epi(ops.EPI_STORE, ws.h3[Nc:]), "w3")
+            ops.swiglu_fwd(ws.h[Nc:], ws.h1[Nc:], ws.h3[Nc:])
+        else:
+            ops.lora_linear_fwd(ws.xm2[Nc:], s1.W, ops.epi(ops.EPI_SWIGLU, ws.h[Nc:], d2=ws.h1[Nc:], d3=ws.h3[Nc:]), W_hi=s3.W)
+        self._linear_fwd_xa(s2, ws.h[Nc:], ops.epi(ops.EPI_GATE_RESID, x_out[Nc:], resid=ws.x2[Nc:], gate=gate_mlp,
+                                                  tokens_per_frame=tpf), "w2")
+        if ex is not None and ex.hidden[b] is not None:
+            x_out[Nc:].add_(ex.hidden[b].to(BF16)[None, :])
+        self._ws_holds = None
 
     # ------------------------------------------------------------------ block backward (dx in ws.dx, in place)
     def _block_bwd(self, b: int, x_in, ex: Optional[Extras]):
@@ -672,21 +755,40 @@ class TTAEngine:
             self.ws.branch_a = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
             self.ws.branch_m = torch.empty(geo.N, self.C, dtype=BF16, device=self.device)
 
-    def forward_tokens(self, text_valid: torch.Tensor, ex: Optional[Extras] = None, stash: bool = False) -> torch.Tensor:
+    def forward_tokens(self, text_valid: torch.Tensor, ex: Optional[Extras] = None, stash: bool = False,
+                       ctx: Optional[str] = None) -> torch.Tensor:
         """ws.P / ws.timestep must hold the patchified input and the per-frame timestep.  Returns ws.pred [N,64] f32
         (final-layer token layout) and leaves the block inputs in ws.xs for the backward.  ``stash``: a backward
-        follows -- keep per-block activations in spare HBM (see _ensure_stash)."""
+        follows -- keep per-block activations in spare HBM (see _ensure_stash).  ``ctx``: "fill" stores every block's
+        context K/V on the way, "use" runs the noised rows only against that cache (forward only, same video / text /
+        adapter state as the fill pass -- the caller guarantees it; see _block_fwd_noise_rows)."""
         ws, geo, C = self.ws, self.geo, self.C
         self._stash_on = False
         if stash:
             self._ensure_stash(geo)
             self._stash_on = True
+        if geo.Nc == 0 or geo.Nn == 0:
+            ctx = None
+        self._ctx_fill = False
+        if ctx is not None:
+            if stash:
+                raise ValueError("the context cache is for forward-only passes")
+            cache = self._ensure_ctx_cache(geo)
+            if ctx == "use" and not cache["valid"]:
+                raise RuntimeError("context cache used before it was filled for this geometry")
+            self._ctx_fill = ctx == "fill"
         pe = self.dit.x_embedder.proj
         ops.gemm(geo.N, C, [(ws.P, pe.weight.view(C, 64), 64, False, None)], ops.epi(ops.EPI_STORE, ws.xs[0], bias=pe.bias))
         self._embed_time()
         self._embed_text(text_valid)
         for b in range(self.L):
-            self._block_fwd(b, ws.xs[b], ws.xs[b + 1], ex)
+            if ctx == "use":
+                self._block_fwd_noise_rows(b, ws.xs[b], ws.xs[b + 1], ex)
+            else:
+                self._block_fwd(b, ws.xs[b], ws.xs[b + 1], ex)
+        if ctx is not None:
+            self._ctx["valid"] = True
+            self._ctx_fill = False
         x_last = ws.xs[self.L]
         if ex is not None and ex.hidden_final is not None:
             x_last.add_(ex.hidden_final.to(BF16)[None, :])

@@ -153,14 +153,16 @@ class TTAStepper:
 
     # ------------------------------------------------------------------ forward-only (anchor loss, common.py:492-559)
     @torch.no_grad()
-    def eval_loss(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
+    def eval_loss(self, cond, target, prompt_embeds, prompt_mask, sigma, noise, ctx: Optional[str] = None) -> torch.Tensor:
+        """ctx: None | "fill" | "use" -- context K/V cache across forwards that share video, text and adapter state
+        (engine._block_fwd_noise_rows)."""
         eng = self.eng
         text_valid = eng.pack_text(prompt_embeds, prompt_mask)
         geo = self._geometry(cond, target, text_valid)
         ex = self.adapter.build_extras() if self.adapter is not None else None
         eng._prepare(geo, ex)
         eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.reshape(-1)[:1].to(F32))
-        eng.forward_tokens(text_valid, ex)
+        eng.forward_tokens(text_valid, ex, ctx=ctx)
         eng._ws_holds = None
         return eng.loss_and_dpred(False).clone()
 

@@ -275,3 +275,39 @@ def test_custom_and_builtin_lora_agree_on_unfused_linears(env):
     assert len(g1) == len(g2) == 2 * len(custom)
     for a, b in zip(g1, g2):
         assert ((a.float() - b.float()).norm() / (a.float().norm() + 1e-30)).item() < 1e-3
+
+
+@pytest.mark.parametrize("method", [None, "delta_a", "film_full_g2"])
+def test_context_cache_reproduces_full_anchor_forwards(env, monkeypatch, method):
+    """Early-stopper anchor grid (3 sigmas x 2 draws on [cond | val]): with the per-block context K/V cache (first
+    forward fills it, the other five run the noised rows only) the loss equals six full forwards."""
+    from longcat_video_tta_b200.common import compute_flow_matching_loss_conditioned_fixed
+    from longcat_video_tta_b200.dit import B200DiT
+    cond, val, prompt = (env[k].to(BF16).cuda() for k in ("cond", "val", "prompt"))
+    mask = env["mask"].cuda()
+    noises = [torch.randn(val.shape, generator=torch.Generator().manual_seed(100 + d)).to(BF16).cuda() for d in range(2)]
+    if method is None:
+        model = B200DiT.from_oracle(env["oracle"])
+    else:
+        model = mine_method(env["oracle"], method)
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for p in model.trainable():
+                p.add_((torch.randn(p.shape, generator=g) * 0.02).to(p.device, p.dtype))
+    calls = []
+    from longcat_video_tta_b200 import engine as E
+    orig = E.TTAEngine.forward_tokens
+
+    def spy(self, text_valid, ex=None, stash=False, ctx=None):
+        calls.append(ctx)
+        return orig(self, text_valid, ex, stash=stash, ctx=ctx)
+
+    monkeypatch.setattr(E.TTAEngine, "forward_tokens", spy)
+    args = (model, cond, val, prompt, mask, [0.25, 0.5, 0.75], noises)
+    cached = compute_flow_matching_loss_conditioned_fixed(*args, device="cuda", dtype=BF16)
+    assert calls == ["fill"] + ["use"] * 5
+    monkeypatch.setenv("B200TTA_NO_CTX_CACHE", "1")
+    full = compute_flow_matching_loss_conditioned_fixed(*args, device="cuda", dtype=BF16)
+    assert calls[6:] == [None] * 6
+    print(f"{method}: anchor loss cached {cached:.7f} full {full:.7f}")
+    assert abs(cached - full) <= 1e-5 * abs(full)
