@@ -166,5 +166,22 @@ class TTAStepper:
         eng._ws_holds = None
         return eng.loss_and_dpred(False).clone()
 
+    @torch.no_grad()
+    def predict_velocity(self, cond, x_t, prompt_embeds, prompt_mask, sigma, ctx: Optional[str] = None) -> torch.Tensor:
+        """Forward only: the predicted velocity of the non-conditioning frames, [1,16,T_gen,H,W] fp32, for an already
+        noised latent ``x_t`` at noise level ``sigma`` (denoise loop; common.py:566-611 via upstream generate_vc)."""
+        eng = self.eng
+        text_valid = eng.pack_text(prompt_embeds, prompt_mask)
+        geo = self._geometry(cond, x_t, text_valid)
+        ex = self.adapter.build_extras() if self.adapter is not None else None
+        eng._prepare(geo, ex)
+        xt = x_t[0].to(BF16)
+        eng.set_inputs(cond[0].to(BF16), xt, xt, sigma.reshape(-1)[:1].to(F32))   # (1 - s) x + s x = x: no re-noising
+        eng.forward_tokens(text_valid, ex, ctx=ctx)
+        eng._ws_holds = None
+        out = torch.empty(16, geo.T, geo.Hl, geo.Wl, dtype=F32, device=eng.device)
+        ops.unpatchify(out, eng.ws.pred, geo.T, geo.Hl, geo.Wl)
+        return out[:, geo.n_cond:].unsqueeze(0).clone()
+
     def total_grad_norm(self) -> torch.Tensor:
         return self.group.tl.total_norm

@@ -340,3 +340,40 @@ def delta_loop(wrapper, params, cond, train, prompt_embeds, prompt_mask, num_ste
         if on_step is not None:
             on_step(step=step, sigma=sigma, noise=noise, loss=loss.detach(), grads=raw)
     return {"losses": losses}
+
+
+# ---------------------------------------------------------------------------------------------------- denoise loop
+def flow_match_sigmas(num_inference_steps, shift=1.0):
+    s = torch.linspace(1.0, 0.0, num_inference_steps + 1, dtype=torch.float64)
+    if shift != 1.0:
+        s = shift * s / (1.0 + (shift - 1.0) * s)
+    return s.to(torch.float32)
+
+
+@torch.no_grad()
+def denoise_latents(dit, cond, prompt_embeds, prompt_mask, init_noise, num_inference_steps, dtype,
+                    negative_prompt_embeds=None, negative_prompt_mask=None, guidance_scale=4.0, shift=1.0):
+    """Flow-matching Euler sampler with classifier-free guidance over FULL forwards of the oracle DiT (no context
+    cache): the checker for longcat_video_tta_b200.denoise.denoise_latents.  The upstream sampler
+    (generate_vc, reached from common.py:566-611) is absent from the reference; this is our statement of it, consistent
+    with the training parametrisation of common.py:458-488 (v = eps - x0 = d x_sigma / d sigma)."""
+    x = init_noise.to(torch.float32).clone()
+    sig = flow_match_sigmas(num_inference_steps, shift)
+    B = cond.shape[0]
+    for k in range(num_inference_steps):
+        s, s_next = float(sig[k]), float(sig[k + 1])
+        sigma = torch.full((B,), s, dtype=torch.float32, device=cond.device)
+        xt = x.to(dtype)
+        hidden, timestep, n_cond = build_step_inputs(cond.to(dtype), xt, sigma, xt, dtype, 1000, _patch_t(dit))
+
+        def vel(pe, pm):
+            pred = dit(hidden_states=hidden, timestep=timestep, encoder_hidden_states=pe.to(dtype),
+                       encoder_attention_mask=pm, num_cond_latents=n_cond)
+            return pred[:, :, cond.shape[2]:].to(torch.float32)
+
+        v = vel(prompt_embeds, prompt_mask)
+        if negative_prompt_embeds is not None and guidance_scale != 1.0:
+            vn = vel(negative_prompt_embeds, negative_prompt_mask)
+            v = vn + guidance_scale * (v - vn)
+        x = x + (s_next - s) * v
+    return x
