@@ -146,6 +146,23 @@ int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, i
                      int32_t heads, float softmax_scale, const b200tta_attn_seg* segs, int32_t n_seg,
                      b200tta_stream_t stream);
 
+/* Block-sparse self-attention for the 720p refinement stage (upstream `enable_bsa` / `bsa_params`, flags at
+ * delta_experiment/scripts/common.py:71-74; the upstream kernel is not vendored -- SURVEY App. A.9 -- so the block
+ * semantics below are OUR definition).  Tokens are in BLOCK-MAJOR order (the 128 tokens of one 3-D chunk are
+ * consecutive; longcat_video_tta_b200.bsa builds the permutation and the lists), n_tok % 128 == 0, one segment.
+ *   q_off [heads * n_blk + 1], q_idx : for (head h, query block i) the ascending key-block indices it attends are
+ *                                      q_idx[q_off[h * n_blk + i] .. q_off[h * n_blk + i + 1])
+ *   k_off / k_idx                    : the transpose (for each key block, the query blocks attending it), backward only.
+ * Everything else as b200tta_attn_fwd / _bwd: the same kernels walk the lists instead of all blocks. */
+int b200tta_attn_bsa_fwd(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                         const void* V, int64_t ldv, int32_t n_tok, int32_t heads, float softmax_scale,
+                         const int32_t* q_off, const int32_t* q_idx, b200tta_stream_t stream);
+int b200tta_attn_bsa_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
+                         int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
+                         int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int32_t n_tok,
+                         int32_t heads, float softmax_scale, const int32_t* q_off, const int32_t* q_idx,
+                         const int32_t* k_off, const int32_t* k_idx, b200tta_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * Fused elementwise / row-reduction kernels (128-bit HBM access, warp-shuffle reductions).
  * Replace the unfused ATen chains of the upstream block.

@@ -66,6 +66,10 @@ struct BwdParams {
     float scale, scale_log2;
     int n_seg;
     int seg_q_begin[MAX_SEGS], seg_q_end[MAX_SEGS], seg_kv_len[MAX_SEGS], seg_item0[MAX_SEGS + 1];
+    // block-sparse variant (NULL = dense): CSR lists over 128-token blocks, tokens in block-major order, one segment.
+    //   q_off [heads * n_qblk + 1] / q_idx : key blocks attended by (head, query block), ascending
+    //   k_off [heads * n_kblk + 1] / k_idx : query blocks that attend (head, key block), ascending (the transpose)
+    const int* q_off; const int* q_idx; const int* k_off; const int* k_idx;
 };
 
 #if B200TTA_ATTN_DEBUG
@@ -198,7 +202,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
     const int q0 = p.seg_q_begin[seg] + (item - p.seg_item0[seg]) * BT;
     const int q_end = p.seg_q_end[seg];
     const int kv_len = p.seg_kv_len[seg];
-    const int n_blk = (kv_len + BT - 1) / BT;
+    int n_blk = (kv_len + BT - 1) / BT;
+    const int* blk_list = nullptr;       // block-sparse: the K/V blocks this (head, query block) attends
+    if (p.q_off != nullptr) {
+        const int o = p.q_off[head * gridDim.x + item];
+        n_blk = p.q_off[head * gridDim.x + item + 1] - o;
+        blk_list = p.q_idx + o;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_k128); tma_prefetch_desc(&p.tma_v128);
@@ -225,24 +235,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
                 const uint32_t ph = (t / STAGES) & 1;
                 mbar_wait(&k_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+                const int kb = blk_list ? blk_list[t] : t;
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(k_s + st * TILE_BYTES + c * HALF_BYTES, &p.tma_k128, &k_full[st], head * D + c * 64, t * BT);
+                    tma_load_2d(k_s + st * TILE_BYTES + c * HALF_BYTES, &p.tma_k128, &k_full[st], head * D + c * 64, kb * BT);
                 mbar_wait(&v_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(v_s + st * TILE_BYTES + c * HALF_BYTES, &p.tma_v128, &v_full[st], head * D + c * 64, t * BT);
+                    tma_load_2d(v_s + st * TILE_BYTES + c * HALF_BYTES, &p.tma_v128, &v_full[st], head * D + c * 64, kb * BT);
             }
         }
     } else if (warp == 1) {
         // one issuer: every poll below sits behind >= 512 clk of queued MMAs (whole warp converged, elected lane issues)
         mbar_wait(qdo_full, 0);
-        mbar_wait2(&k_full[0], 0, &v_full[0], 0);
-        tc_fence_after();
-        mma_ts_n128(t_s, t_q, smem_u32(k_s));
-        umma_commit_e(s_full);
-        mma_ts_n128(t_dp, t_do, smem_u32(v_s));
-        umma_commit_e(dp_full);
-        umma_commit_e(&v_empty[0]);
+        if (n_blk > 0) {
+            mbar_wait2(&k_full[0], 0, &v_full[0], 0);
+            tc_fence_after();
+            mma_ts_n128(t_s, t_q, smem_u32(k_s));
+            umma_commit_e(s_full);
+            mma_ts_n128(t_dp, t_do, smem_u32(v_s));
+            umma_commit_e(dp_full);
+            umma_commit_e(&v_empty[0]);
+        }
         for (int t = 0; t < n_blk; ++t) {
             const int st = t % STAGES, tn = t + 1, st_n = tn % STAGES;
             const uint32_t ph_n = (tn / STAGES) & 1;
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
         for (int t = 0; t < n_blk; ++t) {
             mbar_wait(s_full, t & 1);
             tc_fence_after();
-            const int valid = kv_len - t * BT - c4 * 32;
+            const int valid = blk_list ? 32 : kv_len - t * BT - c4 * 32;   // block-sparse lists only hold whole blocks
             uint32_t sv[32], dp[32], pk[16];
             tmem_ld_32x32b_x32(a_s, sv);
             tmem_ld_wait();
@@ -392,8 +405,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
     constexpr uint32_t t_dv = tmem_base + 256, t_dk = tmem_base + 384;
 
     // every role walks the same list of 64-row query sub-tiles: for each segment that can see this K/V block
+    const int* blk_list = nullptr;       // block-sparse: the query blocks that attend this (head, key block)
+    int n_list = 0;
+    if (p.k_off != nullptr) {
+        const int o = p.k_off[head * gridDim.x + blockIdx.x];
+        n_list = p.k_off[head * gridDim.x + blockIdx.x + 1] - o;
+        blk_list = p.k_idx + o;
+    }
     auto for_each_sub = [&](auto&& fn) {
         int u = 0;
+        if (blk_list != nullptr) {
+            for (int e = 0; e < n_list; ++e) {
+                const int q0 = blk_list[e] * BT;
+                fn(u++, 0, q0);
+                fn(u++, 0, q0 + SUB);
+            }
+            return u;
+        }
         for (int s = 0; s < p.n_seg; ++s) {
             if (kv0 >= p.seg_kv_len[s]) continue;
             for (int q0 = p.seg_q_begin[s]; q0 < p.seg_q_end[s]; q0 += SUB) fn(u++, s, q0);
@@ -401,8 +429,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
         return u;
     };
     int n_sub = 0;
-    for (int s = 0; s < p.n_seg; ++s)
-        if (kv0 < p.seg_kv_len[s]) n_sub += (p.seg_q_end[s] - p.seg_q_begin[s] + SUB - 1) / SUB;
+    if (blk_list != nullptr) n_sub = 2 * n_list;
+    else
+        for (int s = 0; s < p.n_seg; ++s)
+            if (kv0 < p.seg_kv_len[s]) n_sub += (p.seg_q_end[s] - p.seg_q_begin[s] + SUB - 1) / SUB;
 
     if (warp == 0) {
         // whole warp: lane 0 drives TMA, all lanes stage the sub-tile's 64 LSE / delta values (two columns per lane)
@@ -615,11 +645,12 @@ extern "C" int b200tta_debug_read(long long* out32) {
 }
 #endif
 
-extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
-                                int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
-                                int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int32_t n_q,
-                                int32_t n_kv, int32_t heads, float softmax_scale, const b200tta_attn_seg* segs,
-                                int32_t n_seg, b200tta_stream_t stream) {
+static int attn_bwd_impl(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
+                         int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
+                         int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int32_t n_q,
+                         int32_t n_kv, int32_t heads, float softmax_scale, const b200tta_attn_seg* segs,
+                         int32_t n_seg, const int32_t* q_off, const int32_t* q_idx, const int32_t* k_off,
+                         const int32_t* k_idx, b200tta_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     B200_REQUIRE(dQ && dK && dV && dO && O && LSE && delta && Q && K && V && n_q > 0 && n_kv > 0 && heads > 0,
                  "attn_bwd: null/empty argument");
@@ -642,6 +673,7 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
     p.LSE = LSE; p.delta = delta; p.n_q = n_q; p.n_kv = n_kv; p.heads = heads;
     p.scale = softmax_scale; p.scale_log2 = softmax_scale * LOG2E;
     p.n_seg = n_seg;
+    p.q_off = q_off; p.q_idx = q_idx; p.k_off = k_off; p.k_idx = k_idx;
     int items = 0;
     for (int s = 0; s < n_seg; ++s) {
         B200_REQUIRE(segs[s].q_begin >= 0 && segs[s].q_end > segs[s].q_begin && segs[s].q_end <= n_q &&
@@ -669,4 +701,26 @@ extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, 
     if (!B200TTA_ATTN_DEBUG || !getenv("B200TTA_DEBUG_NO_DKV")) dkv_kernel<<<dim3((n_kv + BT - 1) / BT, heads), NUM_THREADS, DKV_SMEM_BYTES, st>>>(p);
     B200_LAUNCHED();
     return B200TTA_OK;
+}
+
+extern "C" int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
+                                int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
+                                int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int32_t n_q,
+                                int32_t n_kv, int32_t heads, float softmax_scale, const b200tta_attn_seg* segs,
+                                int32_t n_seg, b200tta_stream_t stream) {
+    return attn_bwd_impl(dQ, lddq, dK, lddk, dV, lddv, dO, lddo, O, ldo, LSE, delta, Q, ldq, K, ldk, V, ldv, n_q, n_kv, heads,
+                         softmax_scale, segs, n_seg, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int b200tta_attn_bsa_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
+                                    int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta,
+                                    const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv,
+                                    int32_t n_tok, int32_t heads, float softmax_scale, const int32_t* q_off,
+                                    const int32_t* q_idx, const int32_t* k_off, const int32_t* k_idx,
+                                    b200tta_stream_t stream) {
+    B200_REQUIRE(q_off && q_idx && k_off && k_idx, "attn_bsa_bwd: null block list");
+    B200_REQUIRE(n_tok > 0 && n_tok % BT == 0, "attn_bsa_bwd: n_tok=%d must be a multiple of the 128-token block", n_tok);
+    const b200tta_attn_seg seg = {0, n_tok, n_tok};
+    return attn_bwd_impl(dQ, lddq, dK, lddk, dV, lddv, dO, lddo, O, ldo, LSE, delta, Q, ldq, K, ldk, V, ldv, n_tok, n_tok,
+                         heads, softmax_scale, &seg, 1, q_off, q_idx, k_off, k_idx, stream);
 }

@@ -21,13 +21,12 @@ namespace {
 
 constexpr int D = 128;
 constexpr int BM = 128;              // rows per query tile
-constexpr int TILES = 2;             // query tiles per CTA
 constexpr int BN = 128;              // K/V rows per block
 constexpr int KV_STAGES = 2;
 constexpr int TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = two [128 x 64] swizzled sub-tiles
 constexpr int SUB_BYTES = TILE_BYTES / 2;
-constexpr int NUM_THREADS = 32 * (2 + 4 * TILES);
-constexpr int SMEM_BYTES = TILES * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256;
+constexpr int fwd_threads(int tiles) { return 32 * (2 + 4 * tiles); }   // producer, issuer, one softmax warpgroup per tile
+constexpr int fwd_smem(int tiles) { return tiles * TILE_BYTES + 2 * KV_STAGES * TILE_BYTES + 1024 + 256; }
 constexpr int MAX_SEGS = 4;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units
 
@@ -39,6 +38,9 @@ struct FwdParams {
     float scale_log2;  // softmax_scale * log2(e)
     int n_seg;
     int seg_q_begin[MAX_SEGS], seg_q_end[MAX_SEGS], seg_kv_len[MAX_SEGS], seg_item0[MAX_SEGS + 1];
+    // block-sparse variant (NULL = dense; one query tile per CTA): CSR list of the 128-token key blocks attended by
+    // (head, query block), ascending; tokens in block-major order
+    const int* q_off; const int* q_idx;
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -47,7 +49,10 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return y;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_constant__ FwdParams p) {
+// TILES = query tiles per CTA: 2 for dense attention (256 query rows share every K/V tile), 1 for the block-sparse
+// variant (every 128-token query block has its own key-block list).
+template <int TILES>
+__global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_smem = smem;                                   // [TILES][TILE_BYTES]
@@ -73,7 +78,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
     const int q0 = p.seg_q_begin[seg] + (item - p.seg_item0[seg]) * (BM * TILES);
     const int q_end = p.seg_q_end[seg];
     const int kv_len = p.seg_kv_len[seg];
-    const int n_blocks = (kv_len + BN - 1) / BN;
+    int n_blocks = (kv_len + BN - 1) / BN;
+    const int* blk_list = nullptr;
+    if (p.q_off != nullptr) {   // block-sparse (TILES == 1): item = query block
+        const int o = p.q_off[head * gridDim.x + item];
+        n_blocks = p.q_off[head * gridDim.x + item + 1] - o;
+        blk_list = p.q_idx + o;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_q);
@@ -109,14 +120,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_blocks; ++j) {
+                const int kb = blk_list ? blk_list[j] : j;
                 mbar_wait(&k_empty[stage], phase ^ 1u);
                 mbar_arrive_expect_tx(&k_full[stage], TILE_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(k_smem + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_k, &k_full[stage], head * D + c * 64, j * BN);
+                    tma_load_2d(k_smem + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_k, &k_full[stage], head * D + c * 64, kb * BN);
                 mbar_wait(&v_empty[stage], phase ^ 1u);
                 mbar_arrive_expect_tx(&v_full[stage], TILE_BYTES);
                 for (int c = 0; c < 2; ++c)
-                    tma_load_2d(v_smem + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_v, &v_full[stage], head * D + c * 64, j * BN);
+                    tma_load_2d(v_smem + stage * TILE_BYTES + c * SUB_BYTES, &p.tma_v, &v_full[stage], head * D + c * 64, kb * BN);
                 if (++stage == KV_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
@@ -147,6 +159,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
             mbar_wait(&k_full[0], 0);
             tc_fence_after();
             issue_s(0, 0);
+            if (TILES == 1) umma_commit_e(&k_empty[0]);
             int stage = 0;
             uint32_t phase = 0;
             for (int j = 0; j < n_blocks; ++j) {
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
                 if (nstage == KV_STAGES) { nstage = 0; nphase ^= 1u; }
                 mbar_wait(&v_full[stage], phase);
                 for (int t = 0; t < TILES; ++t) {
-                    if (j == 0 && t == 1) {
+                    if (TILES > 1 && j == 0 && t == 1) {
                         // tile 1 starts one softmax later than tile 0: the two softmax groups then run in anti-phase
                         // (one uses the MUFU while the other tile's MMAs run) instead of contending in phase
                         issue_s(1, 0);
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
         for (int j = 0; j < n_blocks; ++j) {
             mbar_wait(&s_full[t], j & 1);
             tc_fence_after();
-            const int valid = kv_len - j * BN;  // columns >= valid are masked (only on the last block)
+            const int valid = blk_list ? BN : kv_len - j * BN;  // columns >= valid are masked (only on the last dense block)
             // the whole 128-column row of S in registers: four back-to-back TMEM loads, one wait
             uint32_t sr[4][32];
 #pragma unroll
@@ -311,10 +324,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_fwd_kernel(const __grid_c
 
 using namespace b200;
 
-extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K,
-                                int64_t ldk, const void* V, int64_t ldv, int32_t n_q, int32_t n_kv, int32_t heads,
-                                float softmax_scale, const b200tta_attn_seg* segs, int32_t n_seg,
-                                b200tta_stream_t stream) {
+static int attn_fwd_impl(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K, int64_t ldk,
+                         const void* V, int64_t ldv, int32_t n_q, int32_t n_kv, int32_t heads, float softmax_scale,
+                         const b200tta_attn_seg* segs, int32_t n_seg, const int32_t* q_off, const int32_t* q_idx,
+                         b200tta_stream_t stream) {
     if (int rc = require_sm100()) return rc;
     B200_REQUIRE(O && LSE && Q && K && V && n_q > 0 && n_kv > 0 && heads > 0, "attn_fwd: null/empty argument");
     B200_REQUIRE(n_seg >= 1 && n_seg <= MAX_SEGS && segs, "attn_fwd: n_seg=%d not in [1,%d]", n_seg, MAX_SEGS);
@@ -322,6 +335,7 @@ extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q,
                      ldk % 8 == 0 && ldv % 8 == 0 && ldq >= (int64_t)heads * D && ldk >= (int64_t)heads * D &&
                      ldv >= (int64_t)heads * D && ldo >= (int64_t)heads * D,
                  "attn_fwd: tensors must be 16-byte aligned [tokens, heads, 128] views");
+    const int tiles = q_off ? 1 : 2;
     FwdParams p;
     memset(&p, 0, sizeof(p));
     if (int rc = make_tmap_2d_bf16(&p.tma_q, Q, (uint64_t)heads * D, (uint64_t)n_q, (uint64_t)ldq * 2, 64, BM)) return rc;
@@ -330,6 +344,7 @@ extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q,
     p.O = (__nv_bfloat16*)O; p.ldo = ldo; p.LSE = LSE; p.n_q = n_q; p.heads = heads;
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.n_seg = n_seg;
+    p.q_off = q_off; p.q_idx = q_idx;
     int items = 0;
     for (int s = 0; s < n_seg; ++s) {
         B200_REQUIRE(segs[s].q_begin >= 0 && segs[s].q_end > segs[s].q_begin && segs[s].q_end <= n_q &&
@@ -337,15 +352,35 @@ extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q,
                      "attn_fwd: bad segment %d [%d,%d) kv %d", s, segs[s].q_begin, segs[s].q_end, segs[s].kv_len);
         p.seg_q_begin[s] = segs[s].q_begin; p.seg_q_end[s] = segs[s].q_end; p.seg_kv_len[s] = segs[s].kv_len;
         p.seg_item0[s] = items;
-        items += (segs[s].q_end - segs[s].q_begin + BM * TILES - 1) / (BM * TILES);
+        items += (segs[s].q_end - segs[s].q_begin + BM * tiles - 1) / (BM * tiles);
     }
     p.seg_item0[n_seg] = items;
     static bool attr = false;
     if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(2)));
+        B200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(1)));
         attr = true;
     }
-    attn_fwd_kernel<<<dim3(items, heads), NUM_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    if (tiles == 2) attn_fwd_kernel<2><<<dim3(items, heads), fwd_threads(2), fwd_smem(2), (cudaStream_t)stream>>>(p);
+    else attn_fwd_kernel<1><<<dim3(items, heads), fwd_threads(1), fwd_smem(1), (cudaStream_t)stream>>>(p);
     B200_LAUNCHED();
     return B200TTA_OK;
+}
+
+extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K,
+                                int64_t ldk, const void* V, int64_t ldv, int32_t n_q, int32_t n_kv, int32_t heads,
+                                float softmax_scale, const b200tta_attn_seg* segs, int32_t n_seg,
+                                b200tta_stream_t stream) {
+    return attn_fwd_impl(O, ldo, LSE, Q, ldq, K, ldk, V, ldv, n_q, n_kv, heads, softmax_scale, segs, n_seg, nullptr, nullptr,
+                         stream);
+}
+
+extern "C" int b200tta_attn_bsa_fwd(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K,
+                                    int64_t ldk, const void* V, int64_t ldv, int32_t n_tok, int32_t heads,
+                                    float softmax_scale, const int32_t* q_off, const int32_t* q_idx,
+                                    b200tta_stream_t stream) {
+    B200_REQUIRE(q_off && q_idx, "attn_bsa_fwd: null block list");
+    B200_REQUIRE(n_tok > 0 && n_tok % BM == 0, "attn_bsa_fwd: n_tok=%d must be a multiple of the 128-token block", n_tok);
+    const b200tta_attn_seg seg = {0, n_tok, n_tok};
+    return attn_fwd_impl(O, ldo, LSE, Q, ldq, K, ldk, V, ldv, n_tok, n_tok, heads, softmax_scale, &seg, 1, q_off, q_idx, stream);
 }

@@ -133,6 +133,20 @@ def attn_bwd(dq, dk, dv, do, o, lse, delta, q, k, v, segs, softmax_scale: float)
           k.shape[0], H, float(softmax_scale), _segs(segs), len(segs), _stream())
 
 
+def attn_bsa_fwd(q, k, v, o, lse, q_off, q_idx, softmax_scale: float):
+    """block-sparse forward: tokens in block-major order, q_off/q_idx int32 CSR lists per (head, query block) -- see bsa.py"""
+    n, H, D = q.shape
+    _call("b200tta_attn_bsa_fwd", _p(o), o.stride(0), _p(lse), _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0),
+          n, H, float(softmax_scale), _p(q_off), _p(q_idx), _stream())
+
+
+def attn_bsa_bwd(dq, dk, dv, do, o, lse, delta, q, k, v, q_off, q_idx, k_off, k_idx, softmax_scale: float):
+    n, H, D = q.shape
+    _call("b200tta_attn_bsa_bwd", _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(do), do.stride(0),
+          _p(o), o.stride(0), _p(lse), _p(delta), _p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), n, H,
+          float(softmax_scale), _p(q_off), _p(q_idx), _p(k_off), _p(k_idx), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ elementwise
 def ln_mod_fwd(y, x, scale, shift, *, tokens_per_frame: int, affine: bool = False, eps: float = 1e-6):
     """modulated: scale/shift f32 [frames, C] views (row stride = adaLN row); affine: weight/bias [C]."""
