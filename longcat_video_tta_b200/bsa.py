@@ -66,12 +66,13 @@ def lists_from_mask(mask: torch.Tensor) -> BlockLists:
 
 
 def select_blocks(q: torch.Tensor, k: torch.Tensor, sparsity: float = 0.9375, n_context_blocks: int = 0) -> BlockLists:
-    """q, k: [n_tok, H, D] in block-major order (after RMSNorm + RoPE).  Returns the block lists of the definition above."""
+    """q, k: [n_tok, H, D] in block-major order (after RMSNorm + RoPE).  Returns the block lists of the definition above.
+    No host synchronisation: every row keeps a number of blocks that is known up front (``row_counts``)."""
     n, H, D = q.shape
     if n % BLOCK:
         raise ValueError(f"n_tok={n} must be a multiple of {BLOCK}")
     nb = n // BLOCK
-    keep = max(1, math.ceil((1.0 - sparsity) * nb))
+    keep, keep_ctx = row_counts(nb, sparsity, n_context_blocks)
     qm = q.reshape(nb, BLOCK, H, D).float().mean(1)       # [nb, H, D]
     km = k.reshape(nb, BLOCK, H, D).float().mean(1)
     score = torch.einsum("ihd,jhd->hij", qm, km)          # [H, nb, nb]
@@ -79,12 +80,29 @@ def select_blocks(q: torch.Tensor, k: torch.Tensor, sparsity: float = 0.9375, n_
     score = score.masked_fill(eye, float("inf"))          # the chunk itself is always kept
     if n_context_blocks > 0:
         score[:, :n_context_blocks, n_context_blocks:] = float("-inf")   # context queries never see noised keys
-    top = score.topk(min(keep, nb), dim=-1).indices
+    top = score.topk(keep, dim=-1).indices
     mask = torch.zeros(H, nb, nb, dtype=torch.bool, device=q.device)
     mask.scatter_(2, top, True)
     if n_context_blocks > 0:
         mask[:, :n_context_blocks, n_context_blocks:] = False
-    return lists_from_mask(mask)
+    nnz = H * (n_context_blocks * keep_ctx + (nb - n_context_blocks) * keep)
+    # query lists: the per-row counts are fixed, so the offsets are analytic
+    counts = torch.full((nb,), keep, dtype=torch.int64)
+    counts[:n_context_blocks] = keep_ctx
+    q_off = torch.zeros(H * nb + 1, dtype=torch.int64)
+    q_off[1:] = torch.cumsum(counts.repeat(H), 0)
+    q_idx = mask.nonzero_static(size=nnz)[:, 2].to(torch.int32).contiguous()
+    mt = mask.transpose(1, 2).contiguous()
+    k_off = torch.zeros(H * nb + 1, dtype=torch.int32, device=q.device)
+    k_off[1:] = torch.cumsum(mt.sum(-1).reshape(-1), 0).to(torch.int32)
+    k_idx = mt.nonzero_static(size=nnz)[:, 2].to(torch.int32).contiguous()
+    return BlockLists(mask, q_off.to(device=q.device, dtype=torch.int32), q_idx, k_off, k_idx)
+
+
+def row_counts(nb: int, sparsity: float, n_context_blocks: int = 0) -> Tuple[int, int]:
+    """(key blocks kept per noised query block, per context query block)"""
+    keep = min(nb, max(1, math.ceil((1.0 - sparsity) * nb)))
+    return keep, (min(keep, n_context_blocks) if n_context_blocks > 0 else keep)
 
 
 def bsa_attention(q, k, v, lists: BlockLists, softmax_scale: Optional[float] = None):

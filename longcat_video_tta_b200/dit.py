@@ -29,7 +29,8 @@ def ffn_hidden_dim(hidden_size: int, mlp_ratio: int = 4, multiple_of: int = 256)
 
 def make_config(name: str = "13.6b", **overrides) -> SimpleNamespace:
     base = dict(in_channels=16, out_channels=16, patch_size=(1, 2, 2), adaln_tembed_dim=512,
-                frequency_embedding_size=256, mlp_ratio=4, text_tokens_zero_pad=True, rope_base=10000.0, norm_eps=1e-6)
+                frequency_embedding_size=256, mlp_ratio=4, text_tokens_zero_pad=True, rope_base=10000.0, norm_eps=1e-6,
+                enable_bsa=False, bsa_params=None)   # bsa_params: dict(sparsity=0.9375, chunk=(4, 4, 8)) -- bsa.py
     if name == "tiny":
         base.update(hidden_size=512, depth=2, num_heads=4, caption_channels=512)
     elif name == "13.6b":
@@ -163,11 +164,11 @@ class B200DiT(nn.Module):
         return m
 
     @classmethod
-    def from_oracle(cls, oracle_dit, device="cuda"):
+    def from_oracle(cls, oracle_dit, device="cuda", **overrides):
         """Copy an ``oracle.dit_oracle.OracleDiT`` (tests only hand one in) into bf16 kernel storage."""
         o = oracle_dit.config
         cfg = make_config("tiny", hidden_size=o.hidden_size, depth=o.depth, num_heads=o.num_heads,
-                          caption_channels=o.caption_channels)
+                          caption_channels=o.caption_channels, **overrides)
         m = cls(cfg)
         missing, unexpected = m.load_state_dict(oracle_dit.state_dict(), strict=False)
         assert not unexpected and not missing, (missing, unexpected)

@@ -215,6 +215,10 @@ class TTAEngine:
         self._site_sig = None
         self.grad_flat: Optional[torch.Tensor] = None
         self._text_cache = None
+        cfgb = getattr(cfg, "bsa_params", None) or {}
+        # block-sparse self-attention (720p refinement stage, configs[4]): see bsa.py for the definition
+        self.bsa = dict(sparsity=float(cfgb.get("sparsity", 0.9375)), chunk=tuple(cfgb.get("chunk", (4, 4, 8)))) \
+            if getattr(cfg, "enable_bsa", False) else None
         self._stash = None          # activation stash of the training geometry (see _ensure_stash)
         self._stash_on = False      # the forward in flight writes / the recompute reads the stash
         self.device = dit.x_embedder.proj.weight.device
@@ -321,6 +325,17 @@ class TTAEngine:
         ws.loss = torch.zeros(1, dtype=F32, device=dev)
         ws.dmod, ws.dmodf, ws.dt = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32), e(T, self.Ct, dt=F32)
         ws.branch_a = ws.branch_m = None  # branch outputs, allocated on demand (FiLM / delta gate gradients)
+        if self.bsa is not None:
+            from . import bsa as _bsa
+            ct = self.bsa["chunk"][0]
+            if geo.n_cond % ct:
+                raise ValueError(f"block-sparse attention needs the context frames ({geo.n_cond}) to be whole chunks of {ct}")
+            ws.bsa_perm, ws.bsa_inv = _bsa.block_permutation(geo.T, geo.gh, geo.gw, self.bsa["chunk"], device=dev)
+            ws.bsa_nctx = geo.Nc // _bsa.BLOCK
+            # block-major copies of q, k, v, o and of their gradients; per-block lists are kept for the backward
+            ws.bq, ws.bk, ws.bv, ws.bo = e(N, C), e(N, C), e(N, C), e(N, C)
+            ws.bdo, ws.bdq, ws.bdk, ws.bdv = e(N, C), e(N, C), e(N, C), e(N, C)
+            ws.bsa_lists = [None] * self.L
         self.ws = ws
         cache[geo] = ws
         self._alloc_lora_ws()
@@ -494,7 +509,10 @@ class TTAEngine:
             self._ctx["k"][b].view(Nc, H, D).copy_(k[:Nc])
             self._ctx["v"][b].view(Nc, H, D).copy_(v[:Nc])
         if not recompute:
-            ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
+            if self.bsa is None:
+                ops.attn_fwd(q, k, v, ws.o.view(N, H, D), ws.lse, geo.self_segments(), self.softmax_scale)
+            else:
+                self._bsa_fwd(b, q, k, v)
         s = st["proj"]
         if recompute and self._stashed(b, "x1") and not keep_branch:
             self._xa_only(s, ws.o, "proj")
@@ -554,6 +572,40 @@ class TTAEngine:
                 self._tap(b, "f_" + nm, getattr(ws, nm))
             self._tap(b, "f_xin", x_in)
             self._tap(b, "f_xout", x_out)
+
+    # ------------------------------------------------------------------ block-sparse self-attention (configs[4])
+    def _bsa_gather(self, q, k, v):
+        ws, N, H, D = self.ws, self.geo.N, self.H, self.D
+        bq, bk, bv = (t.view(N, H, D) for t in (ws.bq, ws.bk, ws.bv))
+        torch.index_select(q, 0, ws.bsa_perm, out=bq)     # (t, h, w) row-major -> block-major token order
+        torch.index_select(k, 0, ws.bsa_perm, out=bk)
+        torch.index_select(v, 0, ws.bsa_perm, out=bv)
+        return bq, bk, bv
+
+    def _bsa_fwd(self, b: int, q, k, v):
+        """self-attention of block b through the list-driven kernels; O comes back in row-major order, LSE stays block-major
+        (only the block-sparse backward reads it) and the block lists are kept for that backward."""
+        from . import bsa as _bsa
+        ws, N, H, D = self.ws, self.geo.N, self.H, self.D
+        bq, bk, bv = self._bsa_gather(q, k, v)
+        lists = _bsa.select_blocks(bq, bk, self.bsa["sparsity"], ws.bsa_nctx)
+        ws.bsa_lists[b] = lists
+        ops.attn_bsa_fwd(bq, bk, bv, ws.bo.view(N, H, D), ws.lse, lists.q_off, lists.q_idx, self.softmax_scale)
+        torch.index_select(ws.bo.view(N, H, D), 0, ws.bsa_inv, out=ws.o.view(N, H, D))
+
+    def _bsa_bwd(self, b: int, dq, dk, dv, do, q, k, v):
+        ws, N, H, D = self.ws, self.geo.N, self.H, self.D
+        lists = ws.bsa_lists[b]
+        bq, bk, bv = self._bsa_gather(q, k, v)
+        bo, bdo = ws.bo.view(N, H, D), ws.bdo.view(N, H, D)
+        torch.index_select(ws.o.view(N, H, D), 0, ws.bsa_perm, out=bo)
+        torch.index_select(do, 0, ws.bsa_perm, out=bdo)
+        bdq, bdk, bdv = (t.view(N, H, D) for t in (ws.bdq, ws.bdk, ws.bdv))
+        ops.attn_bsa_bwd(bdq, bdk, bdv, bdo, bo, ws.lse, ws.delta, bq, bk, bv, lists.q_off, lists.q_idx, lists.k_off,
+                         lists.k_idx, self.softmax_scale)
+        dq.copy_(bdq.index_select(0, ws.bsa_inv))
+        dk.copy_(bdk.index_select(0, ws.bsa_inv))
+        dv.copy_(bdv.index_select(0, ws.bsa_inv))
 
     # ------------------------------------------------------------------ forward with cached context K/V
     # The context (clean conditioning) frames carry timestep 0 and only attend to themselves, so for a fixed video, text
@@ -711,8 +763,11 @@ class TTAEngine:
         dq = ws.dqk.view(N, 2 * H, D)[:, :H]
         dk = ws.dqk.view(N, 2 * H, D)[:, H:]
         dv = ws.dqkv.view(N, 3 * H, D)[:, 2 * H:]
-        ops.attn_bwd(dq, dk, dv, ws.g2.view(N, H, D), ws.o.view(N, H, D), ws.lse, ws.delta, q, k, v,
-                     geo.self_segments(), self.softmax_scale)
+        if self.bsa is None:
+            ops.attn_bwd(dq, dk, dv, ws.g2.view(N, H, D), ws.o.view(N, H, D), ws.lse, ws.delta, q, k, v,
+                         geo.self_segments(), self.softmax_scale)
+        else:
+            self._bsa_bwd(b, dq, dk, dv, ws.g2.view(N, H, D), q, k, v)
         ng = ex is not None and ex.norm_grads
         ops.qk_rmsnorm_rope_bwd(ws.dqkv, ws.dqk, ws.qkv, blk.attn.q_norm.weight, blk.attn.k_norm.weight, H, H,
                                 grid_hw=(geo.gh, geo.gw), rope_base=self.dit.config.rope_base,
@@ -770,6 +825,8 @@ class TTAEngine:
         if geo.Nc == 0 or geo.Nn == 0:
             ctx = None
         self._ctx_fill = False
+        if ctx is not None and self.bsa is not None:
+            ctx = None   # the context K/V cache is implemented for the dense attention path only
         if ctx is not None:
             if stash:
                 raise ValueError("the context cache is for forward-only passes")

@@ -49,3 +49,25 @@ def masked_attention(q, k, v, mask, scale, block=128):
     lse = torch.logsumexp(s, -1)
     o = torch.einsum("hqk,khd->qhd", torch.softmax(s, -1), v)
     return o, lse
+
+
+def block_sparse_attention(q, k, v, shape, num_cond_latents, chunk=(4, 4, 8), sparsity=0.9375):
+    """Self-attention of the oracle DiT under the block-sparse definition.  q, k, v [B, H, N, D] (after q/k norm + RoPE),
+    shape = (T, H', W') token grid, context = the first num_cond_latents frames (must be whole chunks)."""
+    B, H, N, D = q.shape
+    T, Hg, Wg = shape
+    ct, ch, cw = chunk
+    block = ct * ch * cw
+    if num_cond_latents % ct:
+        raise ValueError("the context frames must be whole chunks along T")
+    perm = chunk_permutation(T, Hg, Wg, chunk).to(q.device)
+    n_ctx = (num_cond_latents // ct) * (Hg // ch) * (Wg // cw)
+    outs = []
+    for b in range(B):
+        qb, kb, vb = (t[b][:, perm].transpose(0, 1) for t in (q, k, v))            # [N, H, D] block-major
+        mask = select_mask(qb.detach().float().cpu(), kb.detach().float().cpu(), sparsity, n_ctx, block)
+        o, _ = masked_attention(qb.float(), kb.float(), vb.float(), mask.to(q.device), D ** -0.5, block)
+        ob = torch.empty_like(o)
+        ob[perm] = o                                                                 # back to (t, h, w) row-major
+        outs.append(ob.transpose(0, 1).to(q.dtype))
+    return torch.stack(outs)

@@ -206,7 +206,8 @@ def _sdpa(q, k, v):
 
 
 class Attention(nn.Module):
-    """Appendix A.5.  ``block_sparse`` is an optional (chunk_thw, topk) pair -> A.9."""
+    """Appendix A.5.  ``self.bsa = dict(chunk=(4, 4, 8), sparsity=0.9375)`` switches to the block-sparse variant (A.9,
+    our definition: oracle/bsa_oracle.py)."""
 
     def __init__(self, dim: int, num_heads: int, eps: float, rope_base: float):
         super().__init__()
@@ -216,13 +217,7 @@ class Attention(nn.Module):
         self.k_norm = RMSNormFP32(self.head_dim, eps)
         self.proj = nn.Linear(dim, dim)
         self.rope_3d = RotaryPositionalEmbedding3D(self.head_dim, rope_base)
-        self.bsa = None  # set to dict(chunk=(ct,ch,cw), topk=int) to enable A.9
-
-    def _process_attn(self, q, k, v, shape):
-        if self.bsa is not None:
-            from .bsa_oracle import block_sparse_attention
-            return block_sparse_attention(q, k, v, shape, **self.bsa)
-        return _sdpa(q, k, v)
+        self.bsa = None
 
     def forward(self, x, shape=None, num_cond_latents=None):
         B, N, C = x.shape
@@ -230,14 +225,14 @@ class Attention(nn.Module):
         q, k, v = qkv.unbind(0)  # [B,H,N,D]
         q, k = self.q_norm(q), self.k_norm(k)
         q, k = self.rope_3d(q, k, shape)
-        if num_cond_latents is not None and num_cond_latents > 0:
+        if self.bsa is not None:
+            from .bsa_oracle import block_sparse_attention
+            o = block_sparse_attention(q, k, v, shape, num_cond_latents or 0, **self.bsa)
+        elif num_cond_latents is not None and num_cond_latents > 0:
             nc = num_cond_latents * (N // shape[0])
-            x_cond = self._process_attn(q[:, :, :nc], k[:, :, :nc], v[:, :, :nc], (num_cond_latents,) + tuple(shape[1:]))
-            x_noise = _sdpa(q[:, :, nc:], k, v) if self.bsa is None else \
-                self._process_attn(q[:, :, nc:], k, v, shape)
-            o = torch.cat([x_cond, x_noise], dim=2)
+            o = torch.cat([_sdpa(q[:, :, :nc], k[:, :, :nc], v[:, :, :nc]), _sdpa(q[:, :, nc:], k, v)], dim=2)
         else:
-            o = self._process_attn(q, k, v, shape)
+            o = _sdpa(q, k, v)
         o = o.transpose(1, 2).reshape(B, N, C)
         return self.proj(o)
 

@@ -133,3 +133,65 @@ def test_bsa_at_720p_geometry_slices(ops):
         s = (q[i * 128:(i + 1) * 128, h].float() @ kk.t()) * scale
         close(o[i * 128:(i + 1) * 128, h], torch.softmax(s, -1) @ vv)
         close(lse[h, i * 128:(i + 1) * 128], torch.logsumexp(s, -1), rtol=1e-3)
+
+
+def test_tta_step_with_block_sparse_attention_matches_oracle():
+    """configs[4] on the tiny DiT: 4 context + 4 noised latent frames of 32x32 (2 048 tokens = 16 blocks, sparsity 0.5),
+    LoRA r=8 with non-zero B: loss and adapter gradients of one fused step vs the oracle DiT running the block-sparse
+    definition in plain PyTorch (bf16 and fp32)."""
+    import copy
+    from oracle import tta_oracle as T
+    from oracle.dit_oracle import build_oracle_dit
+    from longcat_video_tta_b200 import lora
+    from longcat_video_tta_b200.dit import B200DiT
+    from longcat_video_tta_b200.stepper import TTAStepper
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    bsa_cfg = dict(chunk=(4, 4, 8), sparsity=0.5)
+    g = torch.Generator().manual_seed(21)
+    cond, train = torch.randn(1, 16, 4, 32, 32, generator=g), torch.randn(1, 16, 4, 32, 32, generator=g)
+    prompt = torch.randn(1, 1, 512, 512, generator=g)
+    mask = torch.zeros(1, 512, dtype=torch.int64)
+    mask[:, :128] = 1
+    sigma, eps = torch.tensor([0.37]), torch.randn(train.shape, generator=g)
+    oracle = build_oracle_dit("tiny", seed=0)
+    dit = B200DiT.from_oracle(oracle, enable_bsa=True, bsa_params=dict(sparsity=0.5))
+    torch.manual_seed(11)
+    mods = lora.inject_lora_into_dit(dit, rank=8, alpha=16.0)
+    refs = {}
+    for name, dtype in (("bf16", BF16), ("fp32", F32)):
+        o = copy.deepcopy(oracle)
+        for blk in o.blocks:
+            blk.attn.bsa = dict(bsa_cfg)
+        torch.manual_seed(11)
+        omods = T.inject_lora(o, rank=8, alpha=16.0)
+        gen = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for m, om in zip(mods, omods):
+                b = (torch.randn(m.lora_up.weight.shape, generator=gen) * 0.02).to(BF16)
+                if name == "bf16":
+                    m.lora_up.weight.copy_(b.cuda())
+                om.lora_up.weight.copy_(b.float())
+                om.lora_down.weight.copy_(m.lora_down.weight.float().cpu())
+        o = o.to(dtype).cuda()
+        params = T.lora_parameters(omods)
+        for p in params:
+            p.requires_grad_(True)
+        cast = (lambda t: t.to(BF16).cuda()) if dtype == BF16 else (lambda t: t.to(BF16).float().cuda())
+        loss = T.fm_loss_given(o, cast(cond), cast(train), cast(prompt), mask.cuda(), sigma.cuda(), cast(eps), dtype)
+        refs[name] = (loss.item(), [x.float() for x in torch.autograd.grad(loss, params)])
+    st = TTAStepper(dit)
+    loss = st.forward_backward(cond.to(BF16).cuda(), train.to(BF16).cuda(), prompt.to(BF16).cuda(), mask.cuda(),
+                               sigma.cuda(), eps.to(BF16).cuda()).item()
+    mine = [g_.float() for site in dit.engine.lora_sites() for g_ in site.param_grads()]
+    lists = dit.engine.ws.bsa_lists[0]
+    assert lists is not None and abs(lists.density - (8 * 8 + 8 * 8) / 256) < 1e-6
+    flat = lambda gs: torch.cat([x.flatten().cpu() for x in gs])
+    cosf = lambda a, b: (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+    c_bf, c_32, c_ref = cosf(flat(mine), flat(refs["bf16"][1])), cosf(flat(mine), flat(refs["fp32"][1])), \
+        cosf(flat(refs["bf16"][1]), flat(refs["fp32"][1]))
+    print(f"BSA step: loss mine {loss:.5f} bf16-torch {refs['bf16'][0]:.5f} fp32 {refs['fp32'][0]:.5f}; grads mine~bf16 {c_bf:.5f} "
+          f"mine~fp32 {c_32:.5f} bf16~fp32 {c_ref:.5f}")
+    assert abs(loss - refs["fp32"][0]) <= 2e-2 * refs["fp32"][0]
+    assert c_bf > 0.999
+    assert c_32 >= min(0.999, c_ref - 5e-3)
