@@ -170,8 +170,15 @@ def run_b200(args):
 
     cfg_name = args.model
     Tc, Tt, Hl, Wl, M = args.cond_frames, args.train_frames, args.lat_h, args.lat_w, args.text_tokens
-    dit = B200DiT.random_init(cfg_name, seed=0, device=dev)
+    bsa_over = {} if args.bsa_sparsity is None else dict(enable_bsa=True, bsa_params=dict(sparsity=args.bsa_sparsity))
+    dit = B200DiT.random_init(cfg_name, seed=0, device=dev, **bsa_over)
     cfg = dit.config
+    if args.bsa_sparsity is not None:   # block-sparse: only the attended 128 x 128 blocks count as algorithmic work
+        from longcat_video_tta_b200 import bsa
+        tpf_ = (Hl // 2) * (Wl // 2)
+        nb, nctx = (Tc + Tt) * tpf_ // bsa.BLOCK, Tc * tpf_ // bsa.BLOCK
+        keep, keep_ctx = bsa.row_counts(nb, args.bsa_sparsity, nctx)
+        _BSA["pairs_per_head"] = float(nctx * keep_ctx + (nb - nctx) * keep) * bsa.BLOCK * bsa.BLOCK
     torch.manual_seed(7)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
@@ -245,6 +252,10 @@ def run_b200(args):
 
     geo = dit.engine.geo
     work = f_alg(cfg.hidden_size, cfg.ffn_dim, cfg.depth, geo.N, geo.Nc, geo.M, 16, lora_sites_qkv_proj)
+    if args.bsa_sparsity is not None:
+        f_attn = 4.0 * cfg.depth * cfg.hidden_size * _BSA["pairs_per_head"]
+        work["total"] += 3.5 * (f_attn - work["f_attn"])
+        work["f_attn"] = f_attn
     peaks = measured_peaks()
     t_step = ms / args.steps / 1000.0
     value = world / t_step
@@ -274,7 +285,9 @@ def run_b200(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {"workload": WORKLOAD if cfg_name == "13.6b" and (Tc, Tt, Hl, Wl, M) == (4, 20, 60, 104, 512) else
-                   f"{cfg_name} LoRA r=16 TTA step, latent [16,{Tc}+{Tt},{Hl},{Wl}], {M} text tokens",
+                   f"{cfg_name} LoRA r=16 TTA step, latent [16,{Tc}+{Tt},{Hl},{Wl}], {M} text tokens"
+                   + ("" if args.bsa_sparsity is None else
+                      f", block-sparse self-attention (128-token chunks 4x4x8, sparsity {args.bsa_sparsity})"),
                    "tokens": geo.N, "adapter_params": stepper.n_params, "parallelism": f"dp{world} over noise draws",
                    "recompute": "per-block forward re-run in the backward except self-attention (O, LSE kept for all blocks) "
                                 "and whatever fits the spare-HBM activation stash (blocks covered: " + _stash_summary(stepper.eng) + ")",
@@ -310,6 +323,9 @@ def _call_flops(name, a):
         return (2.0 * n_tok * fin * fout if has_dx else 0.0) + 2.0 * n_tok * r * (fin + fout) * (3 if has_dx else 2)
     if name == "b200tta_gemm":                 # (M, N, segs, nseg, epi, stream)
         return sum(2.0 * a[0] * a[1] * a[2][i].k for i in range(a[3]))
+    if name in ("b200tta_attn_bsa_fwd", "b200tta_attn_bsa_bwd"):   # 128 x 128 token pairs actually attended (set by main)
+        heads = a[10] if name.endswith("fwd") else a[19]
+        return 4.0 * heads * 128 * _BSA["pairs_per_head"] * (1.0 if name.endswith("fwd") else 2.5)
     if name in ("b200tta_attn_fwd", "b200tta_attn_bwd"):
         segs, n_seg, heads = (a[13], a[14], a[11]) if name.endswith("fwd") else (a[22], a[23], a[20])
         pairs = sum((segs[i].q_end - segs[i].q_begin) * segs[i].kv_len for i in range(n_seg))
@@ -317,8 +333,13 @@ def _call_flops(name, a):
     return None
 
 
+_BSA = {"pairs_per_head": 0.0}
+
+
 def _family(name, a):
     fam = name.replace("b200tta_", "")
+    if fam in ("attn_bsa_fwd", "attn_bsa_bwd"):
+        return fam.replace("_bsa", "") + "[self, block-sparse]"
     if fam in ("attn_fwd", "attn_bwd"):
         n_q, n_kv = (a[9], a[10]) if fam == "attn_fwd" else (a[18], a[19])
         return fam + ("[self]" if n_q == n_kv else "[cross]")
@@ -412,6 +433,8 @@ def main():
     ap.add_argument("--lat-w", type=int, default=104)
     ap.add_argument("--text-tokens", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bsa-sparsity", type=float, default=None,
+                    help="block-sparse self-attention (BASELINE.json configs[4], e.g. 0.9375 with --lat-h 96 --lat-w 160)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
