@@ -55,19 +55,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// suspend-time hint of try_wait: the hardware parks the warp until the phase completes or the hint expires instead of
+// returning early to a software spin loop (fewer issue slots and shared-memory polls burnt by the 16-19 waiting warps
+// of the attention kernels; the step runs under the power cap)
+#ifndef B200TTA_TRYWAIT_HINT_NS
+#define B200TTA_TRYWAIT_HINT_NS 20000u
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(B200TTA_TRYWAIT_HINT_NS)
         : "memory");
     return ok != 0;
 }
 #ifndef B200TTA_SPIN_LIMIT
-#define B200TTA_SPIN_LIMIT (1u << 24)
+#define B200TTA_SPIN_LIMIT (1u << 20)   // x up to 20 us per try_wait: a lost signal traps after at most ~21 s instead of hanging the GPU
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
