@@ -38,7 +38,7 @@ if hasattr(lib, "b200tta_debug_read_fwd"):
     lib.b200tta_debug_read_fwd.argtypes = [C.c_void_p]
     if lib.b200tta_debug_read_fwd(buf) == 0:
         d = list(buf); n = max(d[3], 1)
-        print(f"fwd CTA(0,0): n_blocks {d[3]}; issuer {d[0]/n:.0f} clk/block (wait p_full {d[1]/n:.0f}, k/v_full {d[2]/n:.0f})")
+        print(f"fwd CTA(0,0): n_blocks {d[3]}")
         for off, nm in ((8, "tile0"), (16, "tile1")):
             print(f"  softmax {nm}: {d[off]/n:.0f}/block: wait s_full {d[off+1]/n:.0f}, tmem ld {d[off+2]/n:.0f}, max(+rescale) {d[off+3]/n:.0f}, exp+st+arrive {d[off+4]/n:.0f}")
 if not hasattr(lib, "b200tta_debug_read"):
