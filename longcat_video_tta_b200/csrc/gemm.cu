@@ -12,6 +12,7 @@
 // a rank-r LoRA product is simply one more (short) segment accumulating into the same TMEM tile.
 #include "host_common.h"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace b200 {
 namespace {
@@ -38,6 +39,7 @@ struct alignas(64) GemmParams {
     CUtensorMap tma_a[MAX_SEG];
     CUtensorMap tma_b[MAX_SEG];
     CUtensorMap tma_bhi[MAX_SEG];
+    CUtensorMap tma_b128[MAX_SEG];   // K-major B with a 128-row box: one CTA's half of the N tile in 2-CTA mode
     int k[MAX_SEG];
     int b_mn[MAX_SEG];
     int has_hi[MAX_SEG];
@@ -356,6 +358,225 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
     }
 }
 
+// ------------------------------------------------------------------------------------ 2-CTA form (cta_group::2)
+// A cluster of two CTAs (the two SMs of a TPC) owns a 256 x 256 output tile: CTA r stages rows [128 r, 128 r + 128) of A
+// and HALF of the B tile (N rows [128 r, 128 r + 128)), the leader issues tcgen05.mma.cta_group::2 with M = 256 and the
+// hardware feeds both tensor cores from both shared memories.  Per CTA and k-block that is 8 KB of operand fetch per
+// 128 clk (64 B/clk) plus 32 KB of TMA fill per 512 clk (64 B/clk) -- inside the 128 B/clk of shared memory, where the
+// 1-CTA 128 x 256 tile needs 96 + 94 B/clk (ncu: 74 % tensor-pipe active).  Each CTA drains its own 128 accumulator rows.
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = BM * BK * 2, B2_BYTES = 128 * BK * 2, STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm2_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int BN = 256;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES2 * STAGE2_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES2;
+    uint64_t* tmem_full = empty_bar + STAGES2;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM);
+    const int num_tiles = m_tiles2 * p.n_tiles;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < p.nseg; ++s) {
+            tma_prefetch_desc(&p.tma_a[s]);
+            tma_prefetch_desc(p.b_mn[s] ? &p.tma_b[s] : (p.has_hi[s] ? (rank ? &p.tma_bhi[s] : &p.tma_b[s]) : &p.tma_b128[s]));
+        }
+        for (int i = 0; i < STAGES2; ++i) {
+            mbar_init(&full_bar[i], 1);     // the leader's own arrive.expect_tx; bytes of both CTAs are counted here
+            mbar_init(&empty_bar[i], 1);    // multicast tcgen05.commit of the leader
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);    // multicast tcgen05.commit of the leader
+            mbar_init(&tmem_empty[i], 256); // (leader's copy) the epilogue threads of BOTH CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2cta<512>(tmem_ptr);
+    tc_fence_before();
+    cluster_sync();                         // barrier inits and the TMEM allocation of the peer are visible
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs, own halves)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                int m_blk, n_blk;
+                tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk);
+                const int m0 = m_blk * 2 * BM + rank * BM, n0 = n_blk * BN;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int kblocks = (p.k[s] + BK - 1) / BK;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1u);
+                        uint8_t* sa = smem + stage * STAGE2_BYTES;
+                        uint8_t* sb = sa + A2_BYTES;
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE2_BYTES);
+                        tma_load_2d_2cta(sa, &p.tma_a[s], &full_bar[stage], kb * BK, m0);
+                        if (p.b_mn[s]) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j)
+                                tma_load_2d_2cta(sb + j * (64 * BK * 2), &p.tma_b[s], &full_bar[stage], n0 + (2 * rank + j) * 64, kb * BK);
+                        } else if (p.has_hi[s]) {   // w1 | w3 co-tiling: the leader holds the w1 rows, its peer the w3 rows
+                            tma_load_2d_2cta(sb, rank ? &p.tma_bhi[s] : &p.tma_b[s], &full_bar[stage], kb * BK, n0 / 2);
+                        } else {
+                            tma_load_2d_2cta(sb, &p.tma_b128[s], &full_bar[stage], kb * BK, n0 + rank * 128);
+                        }
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer: leader CTA only
+        if (rank == 0) {
+            constexpr uint32_t idesc_k = umma_idesc_bf16(2 * BM, BN, 0, 0);
+            constexpr uint32_t idesc_mn = umma_idesc_bf16(2 * BM, BN, 0, 1);
+            const uint32_t smem_base = smem_u32(smem);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int kblocks = (p.k[s] + BK - 1) / BK;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(&full_bar[stage], phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+                        const uint32_t sb = sa + A2_BYTES;
+                        const int rem = p.k[s] - kb * BK;
+                        const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
+                        const uint64_t ad = umma_desc_kmajor(sa);
+                        if (p.b_mn[s]) {
+                            const uint64_t bd = umma_desc_mnmajor(sb, 64 * BK * 2);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    umma_ss_2cta_e(d_tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 2048), idesc_mn, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        } else {
+                            const uint64_t bd = umma_desc_kmajor(sb);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    umma_ss_2cta_e(d_tmem, umma_desc_advance(ad, ks * 32), umma_desc_advance(bd, ks * 32), idesc_k, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        }
+                        umma_commit_2cta_e(&empty_bar[stage]);   // frees the slot in BOTH CTAs when these MMAs retire
+                        if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                umma_commit_2cta_e(&tmem_full[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5 of both CTAs, own 128 rows)
+        const int quarter = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int m_blk, n_blk;
+            tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk);
+            const long long row = (long long)m_blk * 2 * BM + rank * BM + quarter * 32 + lane;
+            const int n0 = n_blk * BN;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+            if (p.epi.mode == B200TTA_EPI_SWIGLU) {
+#pragma unroll 1
+                for (int c = 0; c < BN / 64; ++c) {
+                    uint32_t r1[32], r3[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 32, r1);
+                    tmem_ld_32x32b_x32(t_addr + BN / 2 + c * 32, r3);
+                    tmem_ld_wait();
+                    const int col = n0 / 2 + c * 32;
+                    if (row < p.M && col < p.N / 2) {
+                        float h1[32], h3[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { h1[i] = __uint_as_float(r1[i]); h3[i] = __uint_as_float(r3[i]); }
+                        if (p.epi.d2 != nullptr)
+                            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d2) + row * p.epi.ldd2 + col, h1);
+                        if (p.epi.d3 != nullptr)
+                            store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d3) + row * p.epi.ldd3 + col, h3);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) h1[i] = h1[i] / (1.0f + __expf(-h1[i])) * h3[i];
+                        store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d) + row * p.epi.ldd + col, h1);
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_addr + c * 32, r);
+                    tmem_ld_wait();
+                    const int col = n0 + c * 32;
+                    if (row < p.M && col < p.N) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        epilogue_chunk(p.epi, row, col, v);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_leader(&tmem_empty[acc]);   // the leader's issuer waits for both CTAs' epilogues
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();                         // neither CTA may free TMEM / exit while its peer still uses the pair
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2cta<512>(tmem_base);
+    }
+}
+
+int launch2(const GemmParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA(cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+        attr_set = true;
+    }
+    const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM);
+    const int tiles = m_tiles2 * p.n_tiles;
+    const int max_clusters = sm_count() / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM2_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel, p));
+    B200_LAUNCHED();
+    return B200TTA_OK;
+}
+
 template <int BN>
 int launch(const GemmParams& p, cudaStream_t stream) {
     using C = Cfg<BN>;
@@ -415,6 +636,8 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
             if (int rc = make_tmap_2d_bf16(&p.tma_bhi[s], g.b_hi, (uint64_t)g.k, (uint64_t)N / 2, (uint64_t)g.ldb * 2, BK, BN / 2)) return rc;
         } else {
             if (int rc = make_tmap_2d_bf16(&p.tma_b[s], g.b, (uint64_t)g.k, (uint64_t)N, (uint64_t)g.ldb * 2, BK, BN)) return rc;
+            if (BN == 256)
+                if (int rc = make_tmap_2d_bf16(&p.tma_b128[s], g.b, (uint64_t)g.k, (uint64_t)N, (uint64_t)g.ldb * 2, BK, 128)) return rc;
         }
     }
     EpiArgs& e = p.epi;
@@ -433,5 +656,7 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
                      "gemm: SWIGLU_BWD needs h1, h3 (aux1, aux2) and d2");
     B200_REQUIRE(!e.bias || aligned16(e.bias), "gemm: bias alignment");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    static const bool two_cta = getenv("B200TTA_GEMM_2CTA") != nullptr;   // opt-in while the 2-CTA form is being validated
+    if (BN == 256 && two_cta) return launch2(p, st);
     return BN == 256 ? launch<256>(p, st) : launch<64>(p, st);
 }
