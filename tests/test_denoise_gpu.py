@@ -31,7 +31,8 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("adapted", [False, True])
-def test_denoise_latents_match_oracle_sampler(env, adapted):
+def test_denoise_latents_match_oracle_sampler(env, adapted, monkeypatch):
+    monkeypatch.setenv("B200TTA_DETERMINISTIC", "1")   # cached vs full loops are then bit-identical
     from oracle import tta_oracle as T
     from longcat_video_tta_b200 import lora
     from longcat_video_tta_b200.denoise import denoise_latents
@@ -68,11 +69,12 @@ def test_denoise_latents_match_oracle_sampler(env, adapted):
           f"cache vs full forwards {e_cache:.3g}")
     assert torch.isfinite(got).all() and got.shape == noise.shape
     assert e_mine <= 3e-2 and e_mine <= 1.5 * e_torch + 1e-3
-    assert e_cache <= 1e-3
+    assert e_cache <= 1e-3   # bit-identical with B200TTA_DETERMINISTIC=1; the default GEMM only to rounding
 
 
-def test_sigma_schedule_and_single_step_limit(env):
+def test_sigma_schedule_and_single_step_limit(env, monkeypatch):
     """one Euler step from sigma=1 to 0 returns x1 - v(x1): the sampler is the integral of the training target."""
+    monkeypatch.setenv("B200TTA_DETERMINISTIC", "1")   # two forwards are compared
     from longcat_video_tta_b200.denoise import denoise_latents, flow_match_sigmas
     from longcat_video_tta_b200.adapters import stepper_for_eval
     from longcat_video_tta_b200.dit import B200DiT
