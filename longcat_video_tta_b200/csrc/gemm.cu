@@ -46,6 +46,7 @@ struct alignas(64) GemmParams {
     int nseg;
     int M, N;
     int m_tiles, n_tiles;
+    int group_m2;   // M-grouping of the CTA-pair kernel's tile walk (256-row tiles)
     EpiArgs epi;
 };
 
@@ -59,11 +60,11 @@ struct Cfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
-    const int per_group = GROUP_M * n_tiles;
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk, int group_m = GROUP_M) {
+    const int per_group = group_m * n_tiles;
     const int group = tile / per_group;
-    const int first_m = group * GROUP_M;
-    const int rows = min(GROUP_M, m_tiles - first_m);
+    const int first_m = group * group_m;
+    const int rows = min(group_m, m_tiles - first_m);
     const int in_group = tile - group * per_group;
     m_blk = first_m + in_group % rows;
     n_blk = in_group / rows;
@@ -414,7 +415,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm2_kernel(const __grid_con
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
                 int m_blk, n_blk;
-                tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk);
+                tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk, p.group_m2);
                 const int m0 = m_blk * 2 * BM + rank * BM, n0 = n_blk * BN;
                 for (int s = 0; s < p.nseg; ++s) {
                     const int kblocks = (p.k[s] + BK - 1) / BK;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm2_kernel(const __grid_con
         uint32_t acc_phase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
             int m_blk, n_blk;
-            tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk);
+            tile_coords(tile, m_tiles2, p.n_tiles, m_blk, n_blk, p.group_m2);
             const long long row = (long long)m_blk * 2 * BM + rank * BM + quarter * 32 + lane;
             const int n0 = n_blk * BN;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -632,6 +633,7 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
     p.N = (int)N;
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.n_tiles = (int)((N + BN - 1) / BN);
+    { const char* gm = getenv("B200TTA_GEMM_GROUP_M2"); p.group_m2 = gm ? atoi(gm) : 8; }
     for (int s = 0; s < nseg; ++s) {
         const b200tta_gemm_seg& g = segs[s];
         B200_REQUIRE(g.a && g.b && g.k > 0, "gemm: segment %d has null operand or k<=0", s);
