@@ -342,3 +342,28 @@ def test_activation_stash_matches_full_recompute(setup, monkeypatch, target_ffn)
         worst = max(((a - b).norm() / (b.norm() + 1e-30)).item() for a, b in zip(results[label][1], results["off"][1]))
         print(f"stash={label}: worst per-tensor relative L2 difference to full recompute {worst:.3g}")
         assert worst < 1e-3, f"stash={label}: gradient differs from the full recompute"
+
+
+def test_deterministic_switch_gives_the_same_bits_every_run(setup, monkeypatch):
+    """B200TTA_DETERMINISTIC=1 (single-issuer GEMM): two forwards of the same inputs agree bit for bit.  The default
+    CTA-pair GEMM sums its k-blocks in a timing-dependent order, so there the two runs only agree to rounding."""
+    s = setup
+    (sigma, eps), = replay_draws(s["train"], 1)
+    cond, train, prompt = (s[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    mask, sigma = s["mask"].cuda(), sigma.cuda()
+    dit = s["B200DiT"].from_oracle(s["oracle"])
+    lat = torch.cat([cond, train], dim=2)
+    t = torch.full((1, lat.shape[2]), 421.0, device="cuda", dtype=BF16)
+
+    def fwd():
+        with torch.no_grad():
+            return dit(hidden_states=lat, timestep=t, encoder_hidden_states=prompt, encoder_attention_mask=mask)
+
+    monkeypatch.setenv("B200TTA_DETERMINISTIC", "1")
+    a, b = fwd(), fwd()
+    assert torch.equal(a, b)
+    monkeypatch.delenv("B200TTA_DETERMINISTIC")
+    c = fwd()
+    rel = ((c.float() - a.float()).norm() / a.float().norm()).item()
+    print(f"default (CTA-pair) GEMM vs deterministic GEMM forward: rel-L2 {rel:.3g}")
+    assert rel < 5e-3
