@@ -2,10 +2,16 @@
 //
 //   D[M,N] = epilogue( sum_s A_s[M,K_s] * op(B_s) )
 //
-// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// lane) + TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each).  Three pipelines:
-// smem full/empty ring (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue) and the
-// static tile schedule (grouped along M so that a wave of 148 tiles re-uses A and B through L2).
+// Two kernels share the epilogues and the tile walk:
+//   gemm2_kernel   (default for 256-wide N tiles) a CLUSTER OF TWO CTAs owns a 256 x 256 tile: CTA r stages its 128 rows
+//                  of A and half of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) from TWO issuer
+//                  warps that alternate k-blocks, tcgen05.commit multicasts the stage release to both CTAs, each CTA
+//                  drains its own 128 accumulator rows.  See the comment above the kernel for the why.
+//   gemm_kernel<BN> one persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane)
+//                  + TMEM owner, warps 2..5 = epilogue (one TMEM lane quarter each).  Used for N < 256 (BN = 64) and,
+//                  with B200TTA_DETERMINISTIC=1, for everything (fixed summation order).
+// Three pipelines in both: smem full/empty ring (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue) and the
+// static tile schedule (grouped along M so that a wave of tiles re-uses A and B through L2).
 //
 // The K loop runs over up to 4 segments; segment s may present B either K-major ([N,K], forward
 // x @ W^T) or MN-major ([K,N], backward dy @ W -- no transposed copy of the frozen weight), and
