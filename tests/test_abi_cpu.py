@@ -65,3 +65,6 @@ def test_sass_is_blackwell_native():
                           capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
+    # the CTA-pair GEMM: cta_group::2 MMA, 2-CTA TMA loads and the multicast commit
+    for mnemonic in ("UTCHMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass, f"{mnemonic} missing from SASS"
