@@ -43,6 +43,24 @@ struct FwdParams {
     const int* q_off; const int* q_idx;
 };
 
+#ifndef B200TTA_ATTN_DEBUG
+#define B200TTA_ATTN_DEBUG 0
+#endif
+#if B200TTA_ATTN_DEBUG
+// developer timeline (scratch/fwd_timeline.py): SM clock at the hand-over points of one CTA for TL_BLOCKS K/V blocks.
+// slots per block: tile t softmax (warp quarter 0) 5t+{0 s_full seen, 1 S loaded, 2 max done, 3 first half of P
+// signalled, 4 P complete}; issuer 10+3t+{0 p_half seen, 1 p_full seen, 2 next S issued}
+constexpr int TL_J0 = 100, TL_BLOCKS = 24, TL_SLOTS = 16, TL_ITEM = 40;
+__device__ long long g_timeline[TL_BLOCKS * TL_SLOTS];
+#define TL_MARK(cond, j, slot)                                                                             \
+    do {                                                                                                   \
+        if ((cond) && blockIdx.x == TL_ITEM && blockIdx.y == 0 && (j) >= TL_J0 && (j) < TL_J0 + TL_BLOCKS) \
+            g_timeline[((j) - TL_J0) * TL_SLOTS + (slot)] = clock64();                                      \
+    } while (0)
+#else
+#define TL_MARK(cond, j, slot) do { } while (0)
+#endif
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -67,7 +85,8 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
     uint64_t* s_full = v_empty + KV_STAGES;  // TILES
     uint64_t* p_full = s_full + TILES;       // TILES
     uint64_t* o_done = p_full + TILES;       // TILES
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + TILES);
+    uint64_t* p_half = o_done + TILES;       // TILES: first 64 K/V columns of P_t written
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(p_half + TILES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -96,7 +115,7 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int t = 0; t < TILES; ++t) {
-            mbar_init(&s_full[t], 1); mbar_init(&p_full[t], BM); mbar_init(&o_done[t], 1);
+            mbar_init(&s_full[t], 1); mbar_init(&p_full[t], BM); mbar_init(&o_done[t], 1); mbar_init(&p_half[t], BM);
         }
         fence_barrier_init();
     }
@@ -148,10 +167,11 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
                                   umma_desc_advance(kd, c * SUB_BYTES + ks * 32), idesc_s, (c | ks) ? 1u : 0u);
                 umma_commit_e(&s_full[t]);
             };
-            auto issue_pv = [&](int t, int vstage, bool accumulate) {
+            // PV in two halves of 64 K/V rows: the first is issued under the second half of the tile's exponentials
+            auto issue_pv = [&](int t, int vstage, bool accumulate, int half) {
                 const uint64_t vd = umma_desc_mnmajor(v_base + vstage * TILE_BYTES, SUB_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < BN / 16; ++ks)
+                for (int ks = half * 4; ks < half * 4 + 4; ++ks)
                     umma_ts_e(tmem_o0 + t * D, tmem_s0 + t * BN + ks * 8, umma_desc_advance(vd, ks * 2048),
                               idesc_o, (accumulate || ks) ? 1u : 0u);
             };
@@ -174,13 +194,19 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
                         issue_s(1, 0);
                         umma_commit_e(&k_empty[0]);
                     }
+                    mbar_wait(&p_half[t], j & 1);
+                    tc_fence_after();
+                    TL_MARK(lane == 0, j, 10 + 3 * t);
+                    issue_pv(t, stage, j > 0, 0);
                     mbar_wait(&p_full[t], j & 1);
                     tc_fence_after();
-                    issue_pv(t, stage, j > 0);
+                    TL_MARK(lane == 0, j, 11 + 3 * t);
+                    issue_pv(t, stage, j > 0, 1);
                     if (t == TILES - 1) umma_commit_e(&v_empty[stage]);
                     if (j + 1 < n_blocks) {
                         if (t == 0) { mbar_wait(&k_full[nstage], nphase); tc_fence_after(); }
                         issue_s(t, nstage);
+                        TL_MARK(lane == 0, j, 12 + 3 * t);
                         if (t == TILES - 1) umma_commit_e(&k_empty[nstage]);
                     } else {
                         umma_commit_e(&o_done[t]);
@@ -203,12 +229,14 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
         for (int j = 0; j < n_blocks; ++j) {
             mbar_wait(&s_full[t], j & 1);
             tc_fence_after();
+            TL_MARK(quarter == 0 && lane == 0, j, 5 * t);
             const int valid = blk_list ? BN : kv_len - j * BN;  // columns >= valid are masked (only on the last dense block)
             // the whole 128-column row of S in registers: four back-to-back TMEM loads, one wait
             uint32_t sr[4][32];
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(s_addr + c * 32, sr[c]);
             tmem_ld_wait();
+            TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 1);
             // block row maximum (log2 units), four independent chains for ILP
             float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             if (valid >= BN) {
@@ -248,6 +276,7 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
             // segment only) is a separate code path: folded into one loop, ptxas emits a compare + select for EVERY
             // element of every block (+2 of ~4.5 instructions per element).
             const float neg_m = -m;
+            TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 2);
             float ls[4] = {0.f, 0.f, 0.f, 0.f};
             if (valid >= BN) {
 #pragma unroll
@@ -256,12 +285,17 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         const int e = (c & 1) * 16 + i;
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c >> 1][e]), p.scale_log2, neg_m));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c >> 1][e + 1]), p.scale_log2, neg_m));
-                        ls[c & 3] += p0 + p1;
+                        // packed f32x2 FMA / ADD: a warp issues at most one instruction every other clock and stalls 8 clk
+                        // per MUFU, so per element 1 + 8 + 1 + 1 issue clocks instead of 2 + 8 + 2 + 1 (scratch/mufu_rate.cu)
+                        float p0, p1;
+                        ffma2(p0, p1, __uint_as_float(sr[c >> 1][e]), __uint_as_float(sr[c >> 1][e + 1]), p.scale_log2, neg_m);
+                        p0 = fast_exp2(p0);
+                        p1 = fast_exp2(p1);
+                        fadd2(ls[c & 1], ls[2 + (c & 1)], p0, p1);
                         pk[i >> 1] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x8(s_addr + c * 8, pk);
+                    if (c == 3) { tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_half[t]); TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 3); }
                 }
             } else {
 #pragma unroll
@@ -277,6 +311,7 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
                         pk[i >> 1] = pack_bf16x2(p0, p1);
                     }
                     tmem_st_32x32b_x16(s_addr + c * 16, pk);
+                    if (c == 1) { tmem_st_wait(); tc_fence_before(); mbar_arrive(&p_half[t]); }
                 }
             }
             const float lsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
@@ -284,6 +319,7 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&p_full[t]);
+            TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 4);
         }
         // ---- epilogue: O_t / l -> bf16 ; LSE
         mbar_wait(&o_done[t], 0);
@@ -366,6 +402,12 @@ static int attn_fwd_impl(void* O, int64_t ldo, float* LSE, const void* Q, int64_
     B200_LAUNCHED();
     return B200TTA_OK;
 }
+
+#if B200TTA_ATTN_DEBUG
+extern "C" int b200tta_debug_fwd_timeline(long long* host_out) {   // TL_BLOCKS x TL_SLOTS clock values
+    return cudaMemcpyFromSymbol(host_out, b200::g_timeline, sizeof(long long) * 24 * 16) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int b200tta_attn_fwd(void* O, int64_t ldo, float* LSE, const void* Q, int64_t ldq, const void* K,
                                 int64_t ldk, const void* V, int64_t ldv, int32_t n_q, int32_t n_kv, int32_t heads,

@@ -335,6 +335,15 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two elements)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {   // d = a * b + c, b and c broadcast
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %4}; mov.b64 rc, {%5, %5};\n"
+        "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }" : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {   // d += a
+    asm("{ .reg .b64 ra, rd; mov.b64 ra, {%2, %3}; mov.b64 rd, {%0, %1};\n"
+        "add.rn.f32x2 rd, rd, ra; mov.b64 {%0, %1}, rd; }" : "+f"(d0), "+f"(d1) : "f"(a0), "f"(a1));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
