@@ -36,19 +36,27 @@ def _deps_mtime() -> float:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    OBJ.mkdir(parents=True, exist_ok=True)
+    # objects of a developer build (B200TTA_ATTN_DEBUG: timing counters in the attention kernels) live in their own
+    # directory and the library records which flavour it was linked from, so a stale debug object can never end up in
+    # a release library (or the other way round)
+    debug = bool(os.environ.get("B200TTA_ATTN_DEBUG"))
+    obj_dir = CSRC / ("build_debug" if debug else "build")
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    stamp = OBJ / "linked_flavour"
+    flavour = "debug" if debug else "release"
+    relink = not stamp.exists() or stamp.read_text() != flavour
     nvcc = _nvcc()
     hdr_m = _deps_mtime()
     jobs = []
     for src in sources():
-        obj = OBJ / (src.stem + ".o")
+        obj = obj_dir / (src.stem + ".o")
         if force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, hdr_m):
             jobs.append((src, obj))
 
     def compile_one(job):
         src, obj = job
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
-        if os.environ.get("B200TTA_ATTN_DEBUG"):  # developer timing counters in the attention kernels (scratch/bench_attn.py)
+        if debug:
             cmd.insert(1, "-DB200TTA_ATTN_DEBUG=1")
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -62,12 +70,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             for out in ex.map(compile_one, jobs):
                 if verbose and out:
                     print(out, file=sys.stderr)
-    objs = [OBJ / (s.stem + ".o") for s in sources()]
-    if jobs or not LIB.exists():
+    objs = [obj_dir / (s.stem + ".o") for s in sources()]
+    if jobs or relink or not LIB.exists():
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        OBJ.mkdir(parents=True, exist_ok=True)
+        stamp.write_text(flavour)
     return LIB
 
 
