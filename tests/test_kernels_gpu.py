@@ -357,6 +357,25 @@ def test_attn_fwd(ops, n, H, segs):
     close(lse, rl, rtol=1e-3, atol=1e-2)
 
 
+def test_attn_fwd_growing_row_maximum(ops):
+    """Keys whose magnitude jumps from one 128-row K/V block to the next: the running row maximum grows by far more
+    than the 2^8 stale-maximum threshold at blocks 2, 4 and 7, so the forward kernel has to take its O / l rescale
+    path (random N(0,1) inputs never do)."""
+    n, H, D = 1024, 2, 128
+    segs = [(0, 512, 512), (512, 1024, 1024)]
+    qkv = rnd(n, 3, H, D, seed=5).float()
+    f = torch.tensor([0.25, 1.0, 4.0, 0.5, 10.0, 1.0, 2.0, 20.0], device="cuda").repeat_interleave(128)
+    qkv[:, 1] *= f[:, None, None]
+    qkv = qkv.to(BF16)
+    q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
+    o = torch.zeros(n, H, D, dtype=BF16, device="cuda")
+    lse = torch.zeros(H, n, dtype=F32, device="cuda")
+    ops.attn_fwd(q, k, v, o, lse, segs, D ** -0.5)
+    ro, rl = _sdpa_ref(q.float(), k.float(), v.float(), segs, D ** -0.5)
+    close(o, ro)
+    close(lse, rl, rtol=1e-3, atol=1e-2)
+
+
 def test_attn_fwd_cross_attention_shape(ops):
     """queries = noise tokens, keys = 128 packed text tokens (kv [M, 2, H, D])"""
     n, M, H, D = 700, 128, 4, 128
