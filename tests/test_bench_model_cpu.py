@@ -1,0 +1,36 @@
+"""The work model behind bench.py's roofline numbers must reproduce SURVEY.md 8(d)'s figures for BASELINE config 2."""
+import importlib.util
+import pathlib
+
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def bench():
+    spec = importlib.util.spec_from_file_location("bench_module", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)   # main() is guarded by __name__
+    return mod
+
+
+def test_algorithmic_flops_of_the_headline_step(bench):
+    # C=4096, F=11008, L=48, N=37440 (Nc=6240), M=512 text tokens, LoRA r=16 on qkv/proj of self- and cross-attention
+    f = bench.f_alg(4096, 11008, 48, 37440, 6240, 512, 16, bench.lora_sites_qkv_proj)
+    tf = {k: v / 1e12 for k, v in f.items()}
+    assert tf["f_lin"] == pytest.approx(829.5, abs=0.1)     # F_lin 829.5 TFLOP
+    assert tf["f_attn"] == pytest.approx(949.3, abs=0.1)    # F_attn 949.3 (dense would be 1102.4)
+    assert tf["f_x"] == pytest.approx(12.6, abs=0.1)        # F_x 12.6
+    assert tf["f_lora"] == pytest.approx(2.2, abs=0.1)      # F_lora 2.2
+    assert tf["total"] == pytest.approx(5032, abs=2)        # F_alg = 5 032 TFLOP / step
+    # >= 50 % of the 2.25 PFLOP/s nominal dense bf16 peak  <=>  <= 4.47 s/step
+    assert f["total"] / 2.25e15 / 0.5 == pytest.approx(4.47, abs=0.01)
+
+
+def test_lora_sites_cover_the_five_targeted_linears(bench):
+    N, Nn, M, C = 37440, 31200, 512, 4096
+    sites = bench.lora_sites_qkv_proj(N, Nn, M, C)
+    assert len(sites) == 5
+    # rank-16 parameter count per block: (in + out) * r summed over the sites = 851 968
+    assert sum((i + o) * 16 for _, i, o in sites) == 851_968
