@@ -77,10 +77,24 @@ __device__ long long g_dbg[32];
 #define DBG_ON (blockIdx.x == 0 && blockIdx.y == 0)
 #define DBG_CLK() clock64()
 #define DBG_SET(i, v) do { g_dbg[i] = (v); } while (0)
+// developer timeline (scratch/bwd_timeline.py): SM clock at the hand-over points of one CTA of each kernel, TL_N
+// consecutive K/V blocks (dq) / query sub-tiles (dkv) starting at TL_FIRST.  Slots per row: compute warp 0-4, issuer 8-11
+// (see the TL_MARK sites).
+constexpr int TL_CTA = 100, TL_FIRST = 100, TL_N = 24, TL_SLOTS = 16;
+__device__ long long g_tl_dq[TL_N * TL_SLOTS], g_tl_dkv[2 * TL_N * TL_SLOTS];
+#define TL_MARK(buf, first, n, cond, idx, slot)                                                             \
+    do {                                                                                                    \
+        if ((cond) && blockIdx.x == TL_CTA && blockIdx.y == 0 && (idx) >= (first) && (idx) < (first) + (n)) \
+            buf[((idx) - (first)) * TL_SLOTS + (slot)] = clock64();                                          \
+    } while (0)
+#define TL_DQ(cond, t, slot) TL_MARK(g_tl_dq, TL_FIRST, TL_N, cond, t, slot)
+#define TL_DKV(cond, u, slot) TL_MARK(g_tl_dkv, 2 * TL_FIRST, 2 * TL_N, cond, u, slot)
 #else
 #define DBG_ON false
 #define DBG_CLK() 0ll
 #define DBG_SET(i, v) do { } while (0)
+#define TL_DQ(cond, t, slot) do { } while (0)
+#define TL_DKV(cond, u, slot) do { } while (0)
 #endif
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -262,12 +276,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             if (tn < n_blk) {   // S(t+1) as soon as S(t) is in registers
                 mbar_wait2(s_free, t & 1, &k_full[st_n], ph_n);
                 tc_fence_after();
+                TL_DQ(lane == 0, t, 8);      // S(t) released
                 mma_ts_n128(t_s, t_q, smem_u32(k_s + st_n * TILE_BYTES));
                 umma_commit_e(s_full);
                 mbar_wait(&v_full[st_n], ph_n);   // long complete: keeps the poll out of the dQ -> dP path
+                TL_DQ(lane == 0, t, 9);      // S(t+1) issued
             }
             mbar_wait(ds_full, t & 1);
             tc_fence_after();
+            TL_DQ(lane == 0, t, 10);         // dS(t) seen
             mma_ts_k128(t_dq, t_dp, smem_u32(k_s + st * TILE_BYTES));
             umma_commit_e(&k_empty[st]);
             if (tn < n_blk) {   // dP(t+1) overwrites dS(t): ordered behind the dQ MMAs just issued
@@ -275,6 +292,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
                 umma_commit_e(dp_full);
                 umma_commit_e(&v_empty[st_n]);
             }
+            TL_DQ(lane == 0, t, 11);         // dQ(t) and dP(t+1) issued
         }
         umma_commit_e(dq_done);
     } else if (warp >= 3) {
@@ -313,12 +331,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
         for (int t = 0; t < n_blk; ++t) {
             mbar_wait(s_full, t & 1);
             tc_fence_after();
+            TL_DQ(warp == 3 && lane == 0, t, 0);     // S(t) seen
             const int valid = blk_list ? 32 : kv_len - t * BT - c4 * 32;   // block-sparse lists only hold whole blocks
             uint32_t sv[32], dp[32], pk[16];
             tmem_ld_32x32b_x32(a_s, sv);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_free);         // S(t + 1) may overwrite the buffer from here on
+            TL_DQ(warp == 3 && lane == 0, t, 1);     // S(t) loaded and released
             if (valid >= 32) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -330,8 +350,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
                     sv[i] = __float_as_uint(i < valid ? pv : 0.f);
                 }
             }
+            TL_DQ(warp == 3 && lane == 0, t, 2);     // exponentials done
             mbar_wait(dp_full, t & 1);
             tc_fence_after();
+            TL_DQ(warp == 3 && lane == 0, t, 3);     // dP(t) seen
             tmem_ld_32x32b_x32(a_dp, dp);
             tmem_ld_wait();
 #pragma unroll
@@ -342,6 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(ds_full);
+            TL_DQ(warp == 3 && lane == 0, t, 4);     // dS(t) stored and signalled
         }
         mbar_wait(dq_done, 0);
         tc_fence_after();
@@ -503,23 +526,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             else mbar_wait(&p_full[w], j & 1);
             w_ds += DBG_CLK() - c0;
             tc_fence_after();
+            TL_DKV(lane == 0, u, 8);         // P^T(u) seen
             mma_ts_k64(t_dv, tmem_base + w * 128, smem_u32(do_s + st * SUBT_BYTES));
             umma_commit_e(&do_empty[st]);
             if (un < n_sub) {
                 mma_ss_n64(tmem_base + w * 128, ka, smem_u32(q_s + st_n * SUBT_BYTES));
                 umma_commit_e(&s_full[w]);
             }
+            TL_DKV(lane == 0, u, 9);         // dV(u) and S^T(u+2) issued
             c0 = DBG_CLK();
             if (un < n_sub) mbar_wait2(&ds_full[w], j & 1, &do_full[st_n], ph_n);
             else mbar_wait(&ds_full[w], j & 1);
             w_ds += DBG_CLK() - c0;
             tc_fence_after();
+            TL_DKV(lane == 0, u, 10);        // dS^T(u) seen
             mma_ts_k64(t_dk, tmem_base + w * 128 + 64, smem_u32(q_s + st * SUBT_BYTES));
             umma_commit_e(&q_empty[st]);
             if (un < n_sub) {
                 mma_ss_n64(tmem_base + w * 128 + 64, va, smem_u32(do_s + st_n * SUBT_BYTES));
                 umma_commit_e(&dp_full[w]);
             }
+            TL_DKV(lane == 0, u, 11);        // dK(u) and dP^T(u+2) issued
         }
         umma_commit_e(dkv_done);
         if (DBG_ON && warp == 1 && lane == 0) { DBG_SET(16, DBG_CLK() - w_tot0); DBG_SET(17, w_ds); DBG_SET(18, (n_sub + 1) / 2); }
@@ -554,8 +581,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             const uint32_t lse_a = smem_u32(stat_s + st * 2 * SUB + half * 32), dl_a = lse_a + SUB * 4;
             mbar_wait(&stat_full[st], (u / STAGES) & 1);
             long long c1 = DBG_CLK(); w_pre += c1 - c0;
+            TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 0);    // statistics of sub-tile u staged
             mbar_wait(&s_full[g], (u >> 1) & 1);
             tc_fence_after();
+            TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 1);    // S^T(u) seen
             long long c2 = DBG_CLK(); w_sdp += c2 - c1;
             // two passes of 16 columns keep the live set small; a pass stores its bf16 P^T over S^T columns this thread
             // has already consumed.  The 32 probabilities stay in registers for dS^T.
@@ -590,8 +619,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             tc_fence_before();
             mbar_arrive(&p_full[g]);                     // dV(u) can go while dS^T is still being computed
             long long c3 = DBG_CLK(); w_math += c3 - c2;
+            TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 2);    // P^T(u) stored and signalled
             mbar_wait(&dp_full[g], (u >> 1) & 1);
             tc_fence_after();
+            TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 3);    // dP^T(u) seen
 #pragma unroll
             for (int hp = 0; hp < 2; ++hp) {
                 uint32_t dp[16], dk[8];
@@ -610,6 +641,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&ds_full[g]);
+            TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 4);    // dS^T(u) stored and signalled
             w_st += DBG_CLK() - c3;
         });
         if (DBG_ON && warp == 3 && lane == 0) {
@@ -642,6 +674,10 @@ using namespace b200;
 #if B200TTA_ATTN_DEBUG
 extern "C" int b200tta_debug_read(long long* out32) {
     return cudaMemcpyFromSymbol(out32, g_dbg, sizeof(long long) * 32) == cudaSuccess ? 0 : -3;
+}
+extern "C" int b200tta_debug_bwd_timeline(long long* dq_out, long long* dkv_out) {   // [24][16] and [48][16] clock values
+    if (cudaMemcpyFromSymbol(dq_out, g_tl_dq, sizeof(g_tl_dq)) != cudaSuccess) return -3;
+    return cudaMemcpyFromSymbol(dkv_out, g_tl_dkv, sizeof(g_tl_dkv)) == cudaSuccess ? 0 : -3;
 }
 #endif
 
