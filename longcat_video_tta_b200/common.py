@@ -13,7 +13,7 @@ MSE kernels directly.  ``forward_fn`` keeps the reference's seam: when given it 
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import os
 
@@ -46,6 +46,22 @@ def split_tta_latents(latents: torch.Tensor, num_context_latents: int, holdout_f
     train = latents[:, :, t_cond:t_cond + t_train].contiguous()
     val = latents[:, :, t_cond + t_train:].contiguous() if t_val > 0 else None
     return cond, train, val
+
+
+def estimate_tta_split_budget(tta_total_frames: int, tta_context_frames: int, holdout_fraction: float = 0.25,
+                              vae_t_scale: int = 4) -> Dict[str, int]:
+    """Latent split sizes ``split_tta_latents`` will produce for a pixel-frame budget (common.py:1493-1517): same keys."""
+    def latent_len(n_pixel_frames):
+        return 1 + (max(1, int(n_pixel_frames)) - 1) // int(vae_t_scale)
+    t_total, t_ctx = latent_len(tta_total_frames), latent_len(tta_context_frames)
+    t_cond = min(t_ctx, t_total - 1)
+    rest = t_total - t_cond
+    t_val = max(1, int(rest * float(holdout_fraction)))
+    t_train = rest - t_val
+    if t_train < 1:
+        t_train, t_val = rest, 0
+    return {"total_latents": int(t_total), "cond_latents": int(t_cond), "train_latents": int(t_train),
+            "val_latents": int(t_val)}
 
 
 def _draw(target, device, sigma_min, sigma_max):

@@ -55,3 +55,20 @@ def test_split_table_matches_reference_golden(golden_dir):
     for (T, ctx, hf), want in table.items():
         c, t, v = split_tta_latents(torch.zeros(1, 1, T, 1, 1), ctx, hf)
         assert (c.shape[2], t.shape[2], 0 if v is None else v.shape[2]) == want
+
+
+def test_split_budget_matches_reference_golden(golden_dir):
+    """common.py:1493-1517 over 4 140 (total, context, hold-out, VAE scale) settings recorded from the reference, and its
+    agreement with what split_tta_latents actually produces."""
+    import torch
+    from longcat_video_tta_b200.common import estimate_tta_split_budget
+    table = torch.load(golden_dir / "split_budget.pt", weights_only=False)
+    assert len(table) == 4140
+    for (total, ctx, hf, scale), want in table.items():
+        got = estimate_tta_split_budget(total, ctx, holdout_fraction=hf, vae_t_scale=scale)
+        assert got == want, (total, ctx, hf, scale, got, want)
+        if got["total_latents"] >= 2:
+            n_ctx_lat = 1 + (max(1, ctx) - 1) // scale
+            c, t, v = split_tta_latents(torch.zeros(1, 1, got["total_latents"], 1, 1), n_ctx_lat, hf)
+            assert (c.shape[2], t.shape[2], 0 if v is None else v.shape[2]) == \
+                (got["cond_latents"], got["train_latents"], got["val_latents"])
