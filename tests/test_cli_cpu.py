@@ -72,3 +72,18 @@ def test_split_budget_matches_reference_golden(golden_dir):
             c, t, v = split_tta_latents(torch.zeros(1, 1, got["total_latents"], 1, 1), n_ctx_lat, hf)
             assert (c.shape[2], t.shape[2], 0 if v is None else v.shape[2]) == \
                 (got["cond_latents"], got["train_latents"], got["val_latents"])
+
+
+def test_parse_target_blocks_matches_reference_golden(golden_dir):
+    """run_lora_tta.py:263-283 (and its copy in run_delta_b.py) over 72 (spec, depth) pairs, invalid specs included."""
+    import torch
+    from longcat_video_tta_b200.adapters import _parse_target_blocks as parse_adapters
+    table = torch.load(golden_dir / "target_blocks.pt", weights_only=False)
+    for fn, key in ((lora._parse_target_blocks, "lora"), (parse_adapters, "delta_b")):
+        for (spec, n), want in table[key].items():
+            try:
+                r = fn(spec, n)
+                got = None if r is None else sorted(r)
+            except Exception as e:  # noqa: BLE001
+                got = f"raises {type(e).__name__}"
+            assert got == want, (key, spec, n, got, want)
