@@ -109,6 +109,17 @@ def compute_flow_matching_loss_conditioned(dit, cond_latents, target_latents, pr
     return F.mse_loss(pred[:, :, t_cond:].to(torch.float32), (noise - target_latents).to(torch.float32))
 
 
+def _python_mean(vals: List[torch.Tensor]) -> float:
+    """The reference accumulates ``loss.item()`` in a Python float and divides by the count (common.py:528-559); same
+    arithmetic here, after ONE device -> host read of all the per-forward losses instead of one sync per forward."""
+    if not vals:
+        return 0.0
+    total = 0.0
+    for v in torch.cat(vals).tolist():
+        total += v
+    return total / len(vals)
+
+
 def _fused_eval(dit, cond, target, prompt_embeds, prompt_mask, sigma, noise, ctx=None) -> Optional[torch.Tensor]:
     """Forward + MSE through the fused kernels when ``dit`` is a B200DiT or one of our wrappers; device scalar."""
     from .adapters import stepper_for_eval
@@ -145,9 +156,7 @@ def compute_flow_matching_loss_conditioned_fixed(dit, cond_latents, target_laten
                     v = F.mse_loss(pred[:, :, cond_latents.shape[2]:].to(torch.float32),
                                    (noise - target_latents).to(torch.float32)).reshape(1)
             vals.append(v.reshape(1))
-    if not vals:
-        return 0.0
-    return float(torch.cat(vals).mean().item())
+    return _python_mean(vals)
 
 
 def compute_flow_matching_loss_fixed(dit, latents, prompt_embeds, prompt_mask, fixed_sigmas: List[float],
@@ -169,4 +178,4 @@ def compute_flow_matching_loss_fixed(dit, latents, prompt_embeds, prompt_mask, f
                     hidden_states=noisy, timestep=timestep, encoder_hidden_states=prompt_embeds,
                     encoder_attention_mask=prompt_mask)
             vals.append(F.mse_loss(pred.to(torch.float32), (noise - latents).to(torch.float32)).reshape(1))
-    return float(torch.cat(vals).mean().item()) if vals else 0.0
+    return _python_mean(vals)
