@@ -34,67 +34,110 @@ BF16 = torch.bfloat16
 METHODS = ("lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film")
 
 
-def _common_args(p: argparse.ArgumentParser):
-    p.add_argument("--checkpoint-dir", type=str, default=None)
-    p.add_argument("--data-dir", type=str, default=None)
-    p.add_argument("--output-dir", type=str, required=True)
-    p.add_argument("--max-videos", type=int, default=2)
-    p.add_argument("--seed", type=int, default=42)
-    p.add_argument("--device", type=str, default="cuda")
-    p.add_argument("--restart", action="store_true")
-    p.add_argument("--num-cond-frames", type=int, default=14)
-    p.add_argument("--tta-total-frames", type=int, default=None)
-    p.add_argument("--tta-context-frames", type=int, default=None)
-    p.add_argument("--num-frames", type=int, default=28)
-    p.add_argument("--gen-start-frame", type=int, default=14)
-    p.add_argument("--num-inference-steps", type=int, default=50)
-    p.add_argument("--guidance-scale", type=float, default=4.0)
-    p.add_argument("--resolution", type=str, default="480p")
-    p.add_argument("--skip-generation", action="store_true")
-    p.add_argument("--no-save-videos", action="store_true")
-    p.add_argument("--synthetic", action="store_true", help="seeded synthetic latents + random-init DiT")
-    p.add_argument("--model", type=str, default="13.6b", choices=["13.6b", "tiny"])
-    p.add_argument("--latent-hw", type=str, default=None, help="synthetic latent H,W (default 60,104 = 480x832)")
-    add_early_stopping_args(p)
+# ---- the reference's command-line surface, one row per flag: (flag, kind, default[, choices]) with kind in
+# {int, float, str, "on" (store_true), "off:<dest>" (store_false into dest)}.  tests/test_cli_cpu.py holds every row to
+# what the reference's own parsers declare (tests/golden/cli_flags.json <- oracle/make_golden_cli_flags.py).
+_IO = [("--max-videos", int, 100), ("--seed", int, 42), ("--device", str, "cuda")]
+_GENERATION = [("--num-cond-frames", int, 2), ("--num-frames", int, 16), ("--gen-start-frame", int, 32),
+               ("--num-inference-steps", int, 50), ("--guidance-scale", float, 4.0), ("--resolution", str, "480p"),
+               ("--skip-generation", "on", False), ("--no-save-videos", "on", False)]
+_BATCH = [("--batch-videos", int, 1), ("--batch-method", str, "similarity", ["sequential", "similarity"]),
+          ("--retrieval-pool-dir", str, None)]                                   # run_lora_tta.py:716-725
+_AUGMENTATION = [("--aug-enabled", "on", False), ("--aug-flip", "on", False), ("--aug-rotate-deg", float, 10.0),
+                 ("--aug-rotate-random-min", float, 5.0), ("--aug-rotate-random-max", float, 15.0),
+                 ("--aug-rotate-random-count", int, 2), ("--aug-rotate-random-step", float, 1.0),
+                 ("--no-aug-rotate-zoom", "off:aug_rotate_zoom", True), ("--aug-speed-factors", str, "")]   # common.py:1680-1706
+_TTA_FRAMES = [("--tta-total-frames", int, None), ("--tta-context-frames", int, None)]                       # common.py:1404-1417
+_GUARD_MODES = ["fail", "warn", "off"]
+_CAPTION = [("--caption-guard-mode", str, "fail", _GUARD_MODES), ("--caption-guard-min-nonempty-ratio", float, 0.95),
+            ("--caption-guard-min-unique-ratio", float, 0.10), ("--caption-guard-max-top1-ratio", float, 0.50),
+            ("--caption-guard-max-generic-top1-ratio", float, 0.20), ("--caption-guard-topk", int, 5),
+            ("--fixed-caption", str, None),                                      # common.py:1420-1472
+            ("--feature-frame-guard-mode", str, "fail", _GUARD_MODES)]           # common.py:1475-1485
+_ONLINE_EVAL = [("--compute-fvd", "on", False), ("--compute-fid", "on", False), ("--compute-vbench", "on", False),
+                ("--min-fvd-videos", int, 256)]                                  # common.py:2438-2450
+_CLIP_GATE = [("--clip-gate-enabled", "on", False), ("--clip-gate-threshold", float, 0.0),
+              ("--clip-gate-backend", str, "clip", ["clip", "xclip"]),
+              ("--clip-gate-model", str, "openai/clip-vit-large-patch14"), ("--clip-gate-sample-frames", int, 4),
+              ("--clip-gate-aggregation", str, "mean", ["mean", "min", "max"]),
+              ("--clip-gate-sampling-mode", str, "full_window", ["full_window", "late_only"]),
+              ("--clip-gate-late-fraction", float, 0.4), ("--clip-gate-late-only", "on", False),
+              ("--clip-gate-fail-open", "on:clip_gate_fail_open", True),
+              ("--clip-gate-fail-closed", "off:clip_gate_fail_open", True),
+              ("--clip-gate-log-only", "on", False)]                             # common.py:1601-1677
+_METHOD_FLAGS = {
+    "lora": [("--lora-rank", int, 8), ("--lora-alpha", float, 16.0), ("--lora-dropout", float, 0.0),
+             ("--target-ffn", "on", False), ("--target-modules", str, "qkv,proj"), ("--lora-target-blocks", str, "all"),
+             ("--use-builtin-lora", "on", False), ("--save-lora-weights", "on", False), ("--learning-rate", float, 2e-4),
+             ("--num-steps", int, 20), ("--warmup-steps", int, 3), ("--weight-decay", float, 0.01),
+             ("--max-grad-norm", float, 1.0)],                                   # run_lora_tta.py:671-698
+    "delta_a": [("--delta-steps", int, 20), ("--delta-lr", float, 1e-3)],       # run_delta_a.py:376-377
+    "delta_b": [("--delta-steps", int, 20), ("--delta-lr", float, 1e-3), ("--num-groups", int, 4),
+                ("--delta-target", str, "timestep", ["timestep", "hidden"]), ("--delta-dim", int, None),
+                ("--delta-target-blocks", str, "all")],                          # run_delta_b.py:459-473
+    "delta_c": [("--delta-steps", int, 20), ("--delta-lr", float, 1e-3),
+                ("--delta-mode", str, "per_channel", ["per_channel"])],
+    "norm_tune": [("--norm-steps", int, 20), ("--norm-lr", float, 1e-3),
+                  ("--norm-target", str, "all_norm", ["cross_attn_norm", "qk_norm", "all_norm"]),
+                  ("--also-tune-delta", "on", False)],                           # run_norm_tune_tta.py:296-312
+    "film": [("--film-steps", int, 20), ("--film-lr", float, 1e-3),
+             ("--film-mode", str, "full", ["full", "shift_scale", "scale_only"]), ("--num-groups", int, 4)],
+}
+# The reference registers the retrieval-batch flags for LoRA / delta-A only and the CLIP gate for everything except
+# norm-tune / FiLM; the union is accepted everywhere here so that one sweep template drives all methods.
+
+
+def _add_rows(target, rows):
+    for row in rows:
+        flag, kind, default = row[:3]
+        if kind == "on":
+            target.add_argument(flag, action="store_true", default=default)
+        elif isinstance(kind, str) and kind.startswith(("on:", "off:")):
+            target.add_argument(flag, action="store_true" if kind[1] == "n" else "store_false", dest=kind.split(":")[1],
+                                default=default)
+        else:
+            target.add_argument(flag, type=kind, default=default, choices=row[3] if len(row) > 3 else None)
 
 
 def build_parser(method: str) -> argparse.ArgumentParser:
+    """Parser of ``run_<method>`` with the reference's flags, dests, types, defaults and choices.  Deviations, all
+    supersets: ``--checkpoint-dir`` / ``--data-dir`` are required by the reference and only checked here once real-video
+    mode is selected; ``--restart`` is accepted by every method (reference: LoRA / full only); ``--synthetic``,
+    ``--model`` and ``--latent-hw`` are ours."""
     p = argparse.ArgumentParser(description=f"B200-native {method} TTA for LongCat-Video")
-    _common_args(p)
-    if method == "lora":
-        p.add_argument("--lora-rank", type=int, default=8)
-        p.add_argument("--lora-alpha", type=float, default=16.0)
-        p.add_argument("--lora-dropout", type=float, default=0.0)
-        p.add_argument("--target-ffn", action="store_true")
-        p.add_argument("--target-modules", type=str, default="qkv,proj")
-        p.add_argument("--lora-target-blocks", type=str, default="all")
-        p.add_argument("--use-builtin-lora", action="store_true")
-        p.add_argument("--save-lora-weights", action="store_true")
-        p.add_argument("--learning-rate", type=float, default=2e-4)
-        p.add_argument("--num-steps", type=int, default=20)
-        p.add_argument("--warmup-steps", type=int, default=3)
-        p.add_argument("--weight-decay", type=float, default=0.01)
-        p.add_argument("--max-grad-norm", type=float, default=1.0)
-    elif method in ("delta_a", "delta_b", "delta_c"):
-        p.add_argument("--delta-steps", type=int, default=20)
-        p.add_argument("--delta-lr", type=float, default=1e-3)
-        if method == "delta_b":
-            p.add_argument("--num-groups", type=int, default=4)
-            p.add_argument("--delta-target", type=str, default="timestep", choices=["timestep", "hidden"])
-            p.add_argument("--delta-dim", type=int, default=None)
-            p.add_argument("--delta-target-blocks", type=str, default="all")
-        if method == "delta_c":
-            p.add_argument("--delta-mode", type=str, default="per_channel")
-    elif method == "norm_tune":
-        p.add_argument("--norm-steps", type=int, default=20)
-        p.add_argument("--norm-lr", type=float, default=1e-4)
-        p.add_argument("--norm-target", type=str, default="cross_attn_norm", choices=["cross_attn_norm", "qk_norm", "all_norm"])
-    elif method == "film":
-        p.add_argument("--film-steps", type=int, default=20)
-        p.add_argument("--film-lr", type=float, default=1e-3)
-        p.add_argument("--film-mode", type=str, default="full", choices=["full", "shift_scale", "scale_only"])
-        p.add_argument("--num-groups", type=int, default=4)
+    p.add_argument("--checkpoint-dir", type=str, default=None)
+    p.add_argument("--data-dir", type=str, default=None)
+    p.add_argument("--output-dir", type=str, required=True)
+    p.add_argument("--restart", action="store_true")
+    _add_rows(p, _IO)
+    _add_rows(p.add_argument_group(method), _METHOD_FLAGS[method])
+    _add_rows(p.add_argument_group("Video continuation"), _GENERATION)
+    _add_rows(p.add_argument_group("Retrieval-augmented batch TTA"), _BATCH)
+    add_early_stopping_args(p)
+    _add_rows(p.add_argument_group("Data augmentation"), _AUGMENTATION)
+    _add_rows(p.add_argument_group("TTA frames"), _TTA_FRAMES)
+    _add_rows(p.add_argument_group("Caption / feature-frame guards"), _CAPTION)
+    _add_rows(p.add_argument_group("Online distributional metrics"), _ONLINE_EVAL)
+    _add_rows(p.add_argument_group("CLIP gate"), _CLIP_GATE)
+    ours = p.add_argument_group("B200 build")
+    ours.add_argument("--synthetic", action="store_true", help="seeded synthetic latents + random-init DiT")
+    ours.add_argument("--model", type=str, default="13.6b", choices=["13.6b", "tiny"])
+    ours.add_argument("--latent-hw", type=str, default=None, help="synthetic latent H,W (default 60,104 = 480x832)")
     return p
+
+
+def outside_the_step(args) -> Dict:
+    """Flags that configure what sits either side of the TTA step in the reference (pixel-space augmentation, caption /
+    feature guards, CLIP gate, online FVD / FID / VBench, retrieval pool).  They are parsed and written to
+    ``config.json`` like the reference does (run_lora_tta.py:855-908) so that a sweep's records stay comparable; the
+    subsystems themselves need the upstream package and are not part of this build."""
+    v = vars(args)
+    pick = lambda prefix: {k: v[k] for k in sorted(v) if k.startswith(prefix)}  # noqa: E731
+    return {"augmentation": pick("aug_"), "caption_guard": {**pick("caption_guard_"), "fixed_caption": v["fixed_caption"]},
+            "feature_frame_guard_mode": v["feature_frame_guard_mode"], "clip_gate": pick("clip_gate_"),
+            "online_eval": {**pick("compute_"), "min_fvd_videos": v["min_fvd_videos"]},
+            "batch": {"batch_videos": v["batch_videos"], "batch_method": v["batch_method"],
+                      "retrieval_pool_dir": v["retrieval_pool_dir"]}}
 
 
 def frame_budget(args):
@@ -142,6 +185,14 @@ def run(method: str, argv=None) -> Dict:
             "real-video mode needs the upstream VAE / UMT5 / pipeline (out of scope here): encode with the reference's "
             "common.load_longcat_components / encode_video / encode_prompt, load the DiT weights into B200DiT "
             "(INTEGRATION.md 1a) and call longcat_video_tta_b200.lora.finetune_lora_on_conditioning")
+
+    if getattr(args, "also_tune_delta", False):
+        raise NotImplementedError("--also-tune-delta (norm parameters + a delta-A vector in one optimizer, "
+                                  "run_norm_tune_tta.py:380-390) is not wired into the fused step; run norm_tune and "
+                                  "delta_a separately")
+    if args.batch_videos > 1 and method != "lora":
+        raise NotImplementedError("--batch-videos > 1 is built for the LoRA loop only (finetune_lora_batch); the "
+                                  "reference's delta-A batch variant needs the retrieval pool, which is outside the step")
 
     dit = B200DiT.random_init(args.model, seed=0, device=device)
     cfg = dit.config
@@ -196,7 +247,8 @@ def run(method: str, argv=None) -> Dict:
                                                     "guidance_scale": args.guidance_scale, "resolution": args.resolution},
                                      "tta_frames": {"total": total, "context": ctx, "latent_frames": n_lat,
                                                     "context_latents": n_ctx_lat},
-                                     "seed": args.seed, "max_videos": args.max_videos, "synthetic": True, "model": args.model})
+                                     "seed": args.seed, "max_videos": args.max_videos, "synthetic": True, "model": args.model,
+                                     **outside_the_step(args)})
     ckpt_path = out / "checkpoint.json"
     state = {"next_idx": 0, "results": []}
     if ckpt_path.exists() and not args.restart:
@@ -226,11 +278,30 @@ def run(method: str, argv=None) -> Dict:
                 save_fn = (lambda: [p.data.clone() for p in (L.get_lora_parameters(mods) if method == "lora" else wrapper.trainable())])
                 es.setup(model, cond, val, vid["prompt_embeds"], vid["prompt_mask"], device=device, dtype=BF16,
                          video_id=vid["video_name"], save_fn=save_fn)
-            if method == "lora":
+            if method == "lora" and args.batch_videos > 1:
+                # retrieval-augmented batch (run_lora_tta.py:1037-1062 builds it from the pool; here: the evaluation
+                # video + K-1 further synthetic videos), held on the host and visited round-robin
+                batch = []
+                for j in range(args.batch_videos):
+                    nb = vid if j == 0 else synthetic_video(10_000 * j + idx, n_lat, hw, cfg, "cpu")
+                    c_j, t_j, _ = split_tta_latents(nb["latents"], n_ctx_lat, args.es_holdout_fraction)
+                    batch.append({"cond_latents": c_j.cpu(), "train_latents": t_j.cpu(),
+                                  "prompt_embeds": nb["prompt_embeds"].cpu(), "prompt_mask": nb["prompt_mask"].cpu()})
+                result.update({"batch_size": len(batch), "num_neighbors": len(batch) - 1})
+                r = L.finetune_lora_batch(dit, mods, batch, num_steps=args.num_steps, lr=args.learning_rate,
+                                          warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
+                                          max_grad_norm=args.max_grad_norm, device=device, dtype=BF16)
+            elif method == "lora":
+                variants = None
+                if args.aug_enabled and args.aug_flip:
+                    # the reference flips pixel frames before the VAE (common.py augmentation helpers); on synthetic
+                    # latents the mirrored latent stands in so that the variant draw of the loop is exercised
+                    variants = [{"latents": train, "name": "orig"}, {"latents": torch.flip(train, dims=[-1]), "name": "flip"}]
                 r = L.finetune_lora_on_conditioning(dit, mods, cond, train, vid["prompt_embeds"], vid["prompt_mask"],
                                                     num_steps=args.num_steps, lr=args.learning_rate,
                                                     warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
-                                                    max_grad_norm=args.max_grad_norm, device=device, dtype=BF16, early_stopper=es)
+                                                    max_grad_norm=args.max_grad_norm, device=device, dtype=BF16,
+                                                    early_stopper=es, train_latents_variants=variants)
                 if args.save_lora_weights and not args.use_builtin_lora:
                     (out / "lora_weights").mkdir(exist_ok=True)
                     L.save_lora_weights(mods, str(out / "lora_weights" / f"{vid['video_name']}_lora.pt"))

@@ -87,3 +87,94 @@ def test_parse_target_blocks_matches_reference_golden(golden_dir):
             except Exception as e:  # noqa: BLE001
                 got = f"raises {type(e).__name__}"
             assert got == want, (key, spec, n, got, want)
+
+
+@pytest.mark.parametrize("method", ["lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
+def test_flag_surface_matches_reference_golden(golden_dir, method):
+    """Every flag the reference's own parser declares (oracle/make_golden_cli_flags.py executes the parser section of
+    each script's main()) exists here with the same dest, type, default, choices, nargs, const and action class.  The one
+    stated deviation: --checkpoint-dir / --data-dir are required there and checked after parsing here (--synthetic)."""
+    import json
+    golden = json.loads((golden_dir / "cli_flags.json").read_text())[method]
+    ours = {}
+    for a in cli.build_parser(method)._actions:
+        for f in a.option_strings:
+            ours[f] = a
+    assert len(golden) >= 48
+    for g in golden:
+        for f in g["flags"]:
+            assert f in ours, f"{method}: reference flag {f} missing"
+            a = ours[f]
+            got = {"dest": a.dest, "default": a.default, "type": getattr(a.type, "__name__", None) if a.type else None,
+                   "choices": list(a.choices) if a.choices is not None else None, "nargs": a.nargs, "const": a.const,
+                   "action": type(a).__name__, "required": bool(a.required)}
+            want = {k: g[k] for k in got}
+            if f in ("--checkpoint-dir", "--data-dir"):
+                want["required"] = False
+            assert got == want, (method, f, got, want)
+
+
+def test_flags_outside_the_step_are_recorded():
+    a = cli.build_parser("delta_b").parse_args(
+        "--output-dir /tmp/x --clip-gate-enabled --clip-gate-fail-closed --caption-guard-mode warn --compute-fvd "
+        "--aug-enabled --no-aug-rotate-zoom --batch-videos 4 --fixed-caption hello".split())
+    rec = cli.outside_the_step(a)
+    assert rec["clip_gate"]["clip_gate_enabled"] and rec["clip_gate"]["clip_gate_fail_open"] is False
+    assert rec["caption_guard"]["caption_guard_mode"] == "warn" and rec["caption_guard"]["fixed_caption"] == "hello"
+    assert rec["online_eval"]["compute_fvd"] and rec["augmentation"]["aug_rotate_zoom"] is False
+    assert rec["batch"]["batch_videos"] == 4
+
+
+def _stub_engine(monkeypatch, calls):
+    """Replace the GPU pieces of cli.run with recorders so the host control flow (batch assembly, variants, records)
+    runs on the CPU."""
+    import types
+    import torch
+    cfg = types.SimpleNamespace(caption_channels=32, adaln_tembed_dim=512, hidden_size=64, out_channels=16)
+    dit = types.SimpleNamespace(config=cfg, engine=types.SimpleNamespace(resolve_sites=lambda: None))
+    monkeypatch.setattr(cli.B200DiT, "random_init", staticmethod(lambda *a, **k: dit))
+    monkeypatch.setattr(cli.L, "inject_lora_into_dit", lambda d, **kw: ["m0", "m1"])
+    monkeypatch.setattr(cli.L, "count_lora_parameters", lambda mods: {"trainable": 7})
+    monkeypatch.setattr(cli.L, "reset_lora_weights", lambda mods: None)
+
+    def single(d, mods, cond, train, pe, pm, **kw):
+        calls.append(("single", cond.shape[2], train.shape[2], kw.get("train_latents_variants")))
+        return {"losses": [1.0, 0.5], "train_time": 0.1, "es_check_time": 0.0, "early_stopping_info": None}
+
+    def batch(d, mods, batch_data, **kw):
+        calls.append(("batch", batch_data, kw))
+        return {"losses": [1.0] * kw["num_steps"], "train_time": 0.1, "es_check_time": 0.0, "early_stopping_info": None}
+
+    monkeypatch.setattr(cli.L, "finetune_lora_on_conditioning", single)
+    monkeypatch.setattr(cli.L, "finetune_lora_batch", batch)
+    return torch
+
+
+def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch):
+    import json
+    calls = []
+    torch = _stub_engine(monkeypatch, calls)
+    base = (f"--synthetic --model tiny --device cpu --latent-hw 8,8 --tta-total-frames 17 --tta-context-frames 5 "
+            f"--max-videos 1 --es-disable --num-steps 4")
+    s = cli.run("lora", (f"--output-dir {tmp_path / 'b'} {base} --batch-videos 3").split())
+    kind, data, kw = calls[-1]
+    assert kind == "batch" and len(data) == 3 and kw["num_steps"] == 4
+    assert all(d["cond_latents"].device.type == "cpu" and d["cond_latents"].shape[2] == 2 for d in data)
+    assert not torch.equal(data[0]["train_latents"], data[1]["train_latents"])      # neighbours are other videos
+    r = s["results"][0]
+    assert r["success"] and r["batch_size"] == 3 and r["num_neighbors"] == 2 and r["num_train_steps"] == 4
+    cfg = json.loads((tmp_path / "b" / "config.json").read_text())
+    assert cfg["batch"]["batch_videos"] == 3 and cfg["clip_gate"]["clip_gate_fail_open"] is True
+
+    s = cli.run("lora", (f"--output-dir {tmp_path / 'v'} {base} --aug-enabled --aug-flip").split())
+    kind, t_cond, t_train, variants = calls[-1]
+    assert kind == "single" and [v["name"] for v in variants] == ["orig", "flip"]
+    assert torch.equal(variants[1]["latents"], torch.flip(variants[0]["latents"], dims=[-1]))
+    s = cli.run("lora", (f"--output-dir {tmp_path / 'p'} {base}").split())
+    assert calls[-1][3] is None and s["results"][0]["batch_size"] == 1
+
+
+@pytest.mark.parametrize("method,flags", [("norm_tune", "--also-tune-delta"), ("delta_a", "--batch-videos 4")])
+def test_unbuilt_combinations_fail_loudly(tmp_path, method, flags):
+    with pytest.raises(NotImplementedError):
+        cli.run(method, f"--output-dir {tmp_path} --synthetic --model tiny --device cpu {flags}".split())
