@@ -140,6 +140,68 @@ def outside_the_step(args) -> Dict:
                       "retrieval_pool_dir": v["retrieval_pool_dir"]}}
 
 
+def _clip_gate_flat(args) -> Dict:
+    mode = "late_only" if args.clip_gate_late_only else args.clip_gate_sampling_mode
+    return {"clip_gate_enabled": args.clip_gate_enabled, "clip_gate_threshold": args.clip_gate_threshold,
+            "clip_gate_backend": args.clip_gate_backend, "clip_gate_model": args.clip_gate_model,
+            "clip_gate_sample_frames": args.clip_gate_sample_frames, "clip_gate_aggregation": args.clip_gate_aggregation,
+            "clip_gate_sampling_mode": mode, "clip_gate_late_fraction": args.clip_gate_late_fraction,
+            "clip_gate_log_only": args.clip_gate_log_only, "clip_gate_fail_open": args.clip_gate_fail_open}
+
+
+def experiment_config(method: str, args, adapter_cfg: Dict, frames: Dict) -> Dict:
+    """``config.json``.  For LoRA the reference's layout (run_lora_tta.py:855-906: ``method`` = ``lora_tta_<impl>``,
+    ``lora{}``, ``training{}``, ``generation{}``, seed, max_videos, the CLIP-gate settings flat and nested); the delta
+    scripts write no config file in the reference, ours get the same frame.  Additions: ``tta_frames``, ``synthetic``,
+    ``model`` and the recorded-only groups of ``outside_the_step``."""
+    flat = _clip_gate_flat(args)
+    impl = adapter_cfg.get("lora", {}).get("implementation")
+    cfg = {"method": f"lora_tta_{impl}" if method == "lora" else method, **adapter_cfg,
+           "generation": {"num_cond_frames": args.num_cond_frames, "num_frames": args.num_frames,
+                          "gen_start_frame": args.gen_start_frame, "num_inference_steps": args.num_inference_steps,
+                          "guidance_scale": args.guidance_scale, "resolution": args.resolution},
+           "seed": args.seed, "max_videos": args.max_videos, **flat,
+           "tta_frames": frames, "synthetic": True, "model": args.model}
+    rest = outside_the_step(args)
+    rest["clip_gate"] = {k[len("clip_gate_"):]: v for k, v in flat.items()}
+    return {**cfg, **rest}
+
+
+# summary.json: the constant the reference writes under "method" and the hyper-parameters it repeats at the top
+# (run_lora_tta.py:1277-1322, run_delta_a.py:905-, run_delta_b.py:918-955, run_delta_c.py:674-, run_norm_tune_tta.py:631-,
+# run_film_tta.py:676-)
+_SUMMARY_HEAD = {
+    "lora": ("lora_tta", ("lora_rank", "lora_alpha", "learning_rate", "num_steps")),
+    "delta_a": ("delta_a", ("delta_steps", "delta_lr")),
+    "delta_b": ("delta_b", ("delta_target", "delta_target_blocks", "num_groups", "delta_steps", "delta_lr")),
+    "delta_c": ("delta_c", ("delta_mode", "delta_steps", "delta_lr")),
+    "norm_tune": ("norm_tune", ("norm_target", "norm_steps", "norm_lr")),
+    "film": ("film_adapter", ("film_mode", "num_groups", "film_steps", "film_lr")),
+}
+
+
+def summary_record(method: str, args, results: List[Dict]) -> Dict:
+    """``summary.json`` with the reference's keys: averages run over the successful videos and are 0 without any; the
+    generation / CLIP-gate columns exist (0 / empty statistics) because the exporters index them.  ``num_success`` is an
+    alias kept from earlier builds."""
+    ok = [r for r in results if r.get("success", False)]
+    mean = lambda key: (sum(r.get(key) or 0.0 for r in ok) / len(ok)) if ok else 0      # noqa: E731
+    losses = [r["final_loss"] for r in ok if r.get("final_loss") is not None]
+    name, head = _SUMMARY_HEAD[method]
+    gated = [r for r in ok if r.get("clip_gate_enabled")]
+    return {"method": name, **{k: getattr(args, k) for k in head},
+            "num_cond_frames": args.num_cond_frames, "num_frames": args.num_frames, "gen_start_frame": args.gen_start_frame,
+            "batch_videos": args.batch_videos, "retrieval_pool_dir": args.retrieval_pool_dir,
+            "num_videos": len(results), "num_successful": len(ok), "num_failed": len(results) - len(ok),
+            "num_success": len(ok),
+            "avg_train_time": mean("train_time"), "avg_clip_gate_eval_time": mean("clip_gate_eval_time"),
+            "avg_es_check_time": mean("es_check_time"), "avg_gen_time": mean("gen_time"),
+            "avg_total_time": mean("total_time"), "avg_final_loss": (sum(losses) / len(losses)) if losses else 0,
+            **_clip_gate_flat(args),
+            "clip_gate_stats": {"num_enabled": len(gated), "num_scored": 0, "num_skipped": 0, "skip_rate": 0.0},
+            "results": results}
+
+
 def frame_budget(args):
     """run_lora_tta.py:743-758: latent frames used for TTA and the context split."""
     total = args.tta_total_frames or args.num_cond_frames
@@ -240,15 +302,8 @@ def run(method: str, argv=None) -> Dict:
         adapter_cfg = {method: {k: v for k, v in vars(args).items() if k.startswith(("delta", "norm", "film", "num_groups"))},
                        "trainable_params": n_train}
 
-    _save_json(out / "config.json", {"method": method, **adapter_cfg,
-                                     "generation": {"num_cond_frames": args.num_cond_frames, "num_frames": args.num_frames,
-                                                    "gen_start_frame": args.gen_start_frame,
-                                                    "num_inference_steps": args.num_inference_steps,
-                                                    "guidance_scale": args.guidance_scale, "resolution": args.resolution},
-                                     "tta_frames": {"total": total, "context": ctx, "latent_frames": n_lat,
-                                                    "context_latents": n_ctx_lat},
-                                     "seed": args.seed, "max_videos": args.max_videos, "synthetic": True, "model": args.model,
-                                     **outside_the_step(args)})
+    _save_json(out / "config.json", experiment_config(method, args, adapter_cfg, {
+        "total": total, "context": ctx, "latent_frames": n_lat, "context_latents": n_ctx_lat}))
     ckpt_path = out / "checkpoint.json"
     state = {"next_idx": 0, "results": []}
     if ckpt_path.exists() and not args.restart:
@@ -329,10 +384,6 @@ def run(method: str, argv=None) -> Dict:
         state["next_idx"] = idx + 1
         _save_json(ckpt_path, state)
 
-    ok = [r for r in state["results"] if r.get("success")]
-    summary = {"method": method, "num_videos": len(state["results"]), "num_success": len(ok),
-               "avg_train_time": (sum(r["train_time"] for r in ok) / len(ok)) if ok else None,
-               "avg_final_loss": (sum(r["final_loss"] for r in ok) / len(ok)) if ok else None,
-               "results": state["results"]}
+    summary = summary_record(method, args, state["results"])
     _save_json(out / "summary.json", summary)
     return summary

@@ -150,7 +150,7 @@ def _stub_engine(monkeypatch, calls):
     return torch
 
 
-def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch):
+def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch, golden_dir):
     import json
     calls = []
     torch = _stub_engine(monkeypatch, calls)
@@ -164,7 +164,13 @@ def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch):
     r = s["results"][0]
     assert r["success"] and r["batch_size"] == 3 and r["num_neighbors"] == 2 and r["num_train_steps"] == 4
     cfg = json.loads((tmp_path / "b" / "config.json").read_text())
-    assert cfg["batch"]["batch_videos"] == 3 and cfg["clip_gate"]["clip_gate_fail_open"] is True
+    assert cfg["batch"]["batch_videos"] == 3 and cfg["clip_gate"]["fail_open"] is True and cfg["method"] == "lora_tta_custom"
+    layout = json.loads((golden_dir / "output_layout.json").read_text())["lora"]
+    _covers(cfg, layout["config"])                      # the file as written by run(), not only the builder
+    written = json.loads((tmp_path / "b" / "summary.json").read_text())
+    assert [k for k in layout["summary_keys"] if k not in written] == [] and written["num_successful"] == 1
+    ck = json.loads((tmp_path / "b" / "checkpoint.json").read_text())
+    assert set(ck) == {"next_idx", "results"} and ck["next_idx"] == 1
 
     s = cli.run("lora", (f"--output-dir {tmp_path / 'v'} {base} --aug-enabled --aug-flip").split())
     kind, t_cond, t_train, variants = calls[-1]
@@ -178,3 +184,39 @@ def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch):
 def test_unbuilt_combinations_fail_loudly(tmp_path, method, flags):
     with pytest.raises(NotImplementedError):
         cli.run(method, f"--output-dir {tmp_path} --synthetic --model tiny --device cpu {flags}".split())
+
+
+def _covers(have, want, path=""):
+    for k, sub in want.items():
+        assert k in have, f"missing {path}{k}"
+        if isinstance(sub, dict):
+            _covers(have[k], sub, f"{path}{k}.")
+
+
+@pytest.mark.parametrize("method", ["lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
+def test_output_files_carry_the_reference_keys(golden_dir, method):
+    """config.json / summary.json hold every key of the reference's own dict literals (oracle/make_golden_output_layout.py
+    reads them out of each main(); four scripts are cut short in the snapshot, their keys up to the cut are checked) and
+    the same constant under "method"."""
+    import json
+    layout = json.loads((golden_dir / "output_layout.json").read_text())[method]
+    args = cli.build_parser(method).parse_args(["--output-dir", "/tmp/x", "--clip-gate-late-only"])
+    results = [{"idx": 0, "success": True, "train_time": 2.0, "es_check_time": 1.0, "final_loss": 0.5, "total_time": 4.0},
+               {"idx": 1, "success": True, "train_time": 4.0, "es_check_time": 0.0, "final_loss": 1.5, "total_time": 6.0},
+               {"idx": 2, "success": False, "error": "x"}]
+    s = cli.summary_record(method, args, results)
+    assert s["method"] == layout["summary_method"]
+    assert [k for k in layout["summary_keys"] if k not in s] == []
+    assert (s["num_videos"], s["num_successful"], s["num_failed"]) == (3, 2, 1)
+    assert (s["avg_train_time"], s["avg_es_check_time"], s["avg_total_time"], s["avg_final_loss"], s["avg_gen_time"]) == \
+        (3.0, 0.5, 5.0, 1.0, 0.0)
+    assert s["clip_gate_sampling_mode"] == "late_only" and s["results"] is results
+    empty = cli.summary_record(method, args, [])
+    assert empty["avg_train_time"] == 0 and empty["avg_final_loss"] == 0 and empty["num_successful"] == 0
+    json.dumps(s)
+    if layout["config"]:
+        adapter = {"lora": {k: 0 for k in layout["config"]["lora"]}, "training": {k: 0 for k in layout["config"]["training"]}}
+        adapter["lora"]["implementation"] = "builtin"
+        cfg = cli.experiment_config(method, args, adapter, {"total": 2})
+        _covers(cfg, layout["config"])
+        assert cfg["method"] == "lora_tta_builtin" and cfg["clip_gate"]["sampling_mode"] == "late_only"
