@@ -134,6 +134,31 @@ def cpu_sample(steps: int, warmup: int, threads: int):
                         f"algorithmic-FLOP ratio {scale:.0f}x to whole steps"))
 
 
+def cpu_tiny_sample(threads: int, steps: int = 5, warmup: int = 1):
+    """BASELINE.json configs[0] as the reference can run it on a CPU (SURVEY 8d "CPU baseline timed beside it"): the tiny
+    DiT (2 blocks, hidden 512), LoRA r=16 on qkv,proj, 17-frame 256x256 latent split 2 / 2 / 1, fp32, the whole LoRA loop
+    of the oracle port (noise draw, forward, adapter backward, clip, AdamW).  Median seconds per step, not scaled."""
+    import torch
+    from oracle.dit_oracle import build_oracle_dit
+    from oracle.make_golden import tiny_inputs, tiny_split
+    from oracle import tta_oracle as T
+    torch.set_num_threads(threads)
+    latents, prompt, mask = tiny_inputs()
+    cond, train, _ = tiny_split(latents)
+    dit = build_oracle_dit("tiny", seed=0)
+    torch.manual_seed(7)
+    mods = T.inject_lora(dit, rank=16, alpha=32.0)
+    stamps = [time.perf_counter()]
+    torch.manual_seed(42)
+    T.lora_tta_loop(dit, mods, cond, train, prompt, mask, num_steps=warmup + steps, lr=2e-4, warmup_steps=3,
+                    on_step=lambda **kw: stamps.append(time.perf_counter()))
+    per = sorted([b - a for a, b in zip(stamps[:-1], stamps[1:])][warmup:])
+    t = per[len(per) // 2]
+    return {"value": 1.0 / t, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"configs[0]: tiny DiT LoRA r=16 TTA step on a 17-frame 256x256 latent (1024 tokens), fp32, oracle port on "
+                      f"{threads} threads, {warmup} warm-up + {steps} timed steps, median {t * 1e3:.0f} ms/step (unscaled)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -275,10 +300,11 @@ def run_b200(args):
                 "peak_source": peaks["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
                 "launches_per_step": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                 "algorithmic_tflop_per_launch": d["flops"] / d["n"] / 1e12, "share_of_step": d["ms"] / tot_ms}
-    cpu = None
+    cpu = cpu_tiny = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_sample(2, 1, os.cpu_count() or 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": r["sample"]}
+        cpu_tiny = cpu_tiny_sample(os.cpu_count() or 1)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -298,6 +324,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
+        "cpu_baseline_config0": cpu_tiny,
         "algorithmic_tflop_per_step": work["total"] / 1e12,
         "achieved_tflops_per_gpu": tflops,
         "frac_of_nominal_2250": tflops / 2250.0,

@@ -34,3 +34,11 @@ def test_lora_sites_cover_the_five_targeted_linears(bench):
     assert len(sites) == 5
     # rank-16 parameter count per block: (in + out) * r summed over the sites = 851 968
     assert sum((i + o) * 16 for _, i, o in sites) == 851_968
+
+
+def test_config0_cpu_leg_runs_the_oracle_loop():
+    """bench.py's configs[0] CPU leg (tiny DiT, fp32, oracle port) returns a rate with its core count and sample stated."""
+    import bench
+    r = bench.cpu_tiny_sample(2, steps=2, warmup=0)
+    assert r["kind"] == "port" and r["cores"] == 2 and r["unit"] == bench.UNIT and r["value"] > 0
+    assert "configs[0]" in r["sample"] and "2 timed steps" in r["sample"]
