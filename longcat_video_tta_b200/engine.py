@@ -63,14 +63,35 @@ class Geometry:
 
 
 # ---------------------------------------------------------------------------------------------------- adapter sites
+def _hooked_lora(module: nn.Module):
+    """The builtin-style ``LoRAModule`` attached to a plain linear: ours carry it as ``._b200_lora``; the reference's own
+    ``inject_builtin_lora_into_dit`` keeps ``module.org_forward`` and replaces ``module.forward`` by a closure over the
+    ``LoRAModule`` (run_lora_tta.py:137-140,173-182) -- found there, so that its injection works on a B200DiT unchanged."""
+    lora = getattr(module, "_b200_lora", None)
+    if lora is not None:
+        return lora
+    fwd = module.__dict__.get("forward")
+    if fwd is None or not hasattr(module, "org_forward"):
+        return None
+    for cell in getattr(fwd, "__closure__", None) or ():
+        try:
+            obj = cell.cell_contents
+        except ValueError:
+            continue
+        if all(hasattr(obj, a) for a in ("lora_down", "lora_up", "multiplier", "alpha_scale")):
+            return obj
+    return None
+
+
 class LinearSite:
     """One linear of the block as the kernels see it: frozen W / bias plus an optional rank-r adapter.
 
     Recognised adapter forms (duck-typed):
       * a wrapper with ``.original`` / ``.lora_down`` / ``.lora_up`` / ``.scaling``  (reference ``LoRALinear``,
         run_lora_tta.py:224-260, or ours);
-      * a plain ``nn.Linear`` carrying ``._b200_lora`` (builtin-style ``LoRAModule``: ``lora_down`` [n_sep*r, in],
-        ``lora_up`` Linear or ``.blocks[i]``, ``multiplier * alpha_scale``; run_lora_tta.py:132-135,175-181).
+      * a plain ``nn.Linear`` carrying ``._b200_lora`` or the reference's hooked ``forward`` (builtin-style
+        ``LoRAModule``: ``lora_down`` [n_sep*r, in], ``lora_up`` Linear or ``.blocks[i]``, ``multiplier * alpha_scale``;
+        run_lora_tta.py:132-140,175-181).
     """
 
     def __init__(self, module: nn.Module, name: str):
@@ -87,8 +108,8 @@ class LinearSite:
             self.scale = float(getattr(module, "scaling", 1.0))
             if getattr(module, "dropout", None) is not None and isinstance(module.dropout, nn.Dropout) and module.dropout.p > 0:
                 raise NotImplementedError("LoRA dropout > 0 is not supported by the fused kernels (reference default is 0.0)")
-        elif getattr(module, "_b200_lora", None) is not None:
-            lora = module._b200_lora
+        elif _hooked_lora(module) is not None:
+            lora = _hooked_lora(module)
             if getattr(lora, "use_lora", True):
                 down, up = lora.lora_down, lora.lora_up
                 self.scale = float(lora.multiplier) * float(lora.alpha_scale)
@@ -231,7 +252,7 @@ class TTAEngine:
         for blk in self.dit.blocks:
             for m in (blk.attn.qkv, blk.attn.proj, blk.cross_attn.q_linear, blk.cross_attn.kv_linear, blk.cross_attn.proj,
                       blk.ffn.w1, blk.ffn.w2, blk.ffn.w3):
-                sig.append((id(m), id(getattr(m, "_b200_lora", None))))
+                sig.append((id(m), id(_hooked_lora(m))))
         return tuple(sig)
 
     def resolve_sites(self, force: bool = False):
