@@ -202,6 +202,22 @@ def summary_record(method: str, args, results: List[Dict]) -> Dict:
             "results": results}
 
 
+def training_record(method: str, args, r: Dict) -> Dict:
+    """Per-video fields that come out of the optimisation loop, with the method-specific ones the reference records
+    (run_delta_a.py:763-775 ``delta_norm``, run_delta_b.py:757-768 ``delta_norms`` + ``num_groups``, run_delta_c.py:531-541
+    ``delta_out_norm``, run_film_tta.py:584-593 ``correction_norm``); ``losses`` and ``num_train_steps`` on every method
+    are additions."""
+    rec = {"train_time": r["train_time"], "es_check_time": r.get("es_check_time", 0.0),
+           "final_loss": r["losses"][-1] if r["losses"] else None, "num_train_steps": len(r["losses"]), "losses": r["losses"]}
+    for key in ("delta_norm", "delta_norms", "delta_out_norm", "correction_norm"):
+        if key in r:
+            rec[key] = r[key]
+    if method == "delta_b":
+        rec["num_groups"] = args.num_groups
+    rec.update({"early_stopping_info": r.get("early_stopping_info"), "success": True})
+    return rec
+
+
 def frame_budget(args):
     """run_lora_tta.py:743-758: latent frames used for TTA and the context split."""
     total = args.tta_total_frames or args.num_cond_frames
@@ -374,9 +390,7 @@ def run(method: str, argv=None) -> Dict:
                            device=device, early_stopper=es)
                 r.setdefault("train_time", time.time() - t0)
                 r.setdefault("es_check_time", 0.0)
-            result.update({"train_time": r["train_time"], "es_check_time": r.get("es_check_time", 0.0),
-                           "final_loss": r["losses"][-1] if r["losses"] else None, "num_train_steps": len(r["losses"]),
-                           "losses": r["losses"], "early_stopping_info": r.get("early_stopping_info"), "success": True})
+            result.update(training_record(method, args, r))
         except Exception as e:  # per-video failure is recorded and the run continues (run_lora_tta.py:1264-1271)
             result.update({"success": False, "error": f"{type(e).__name__}: {e}"})
         result["total_time"] = time.time() - t_video

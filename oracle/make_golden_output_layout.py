@@ -7,7 +7,8 @@ of every ``main()``: run_lora_tta.py:1277-1322, run_delta_a.py:905-, run_delta_b
 run_norm_tune_tta.py:631-, run_film_tta.py:676-) are dict literals inside ``main()``, which cannot be executed here
 (checkpoints, datasets).  Their KEYS -- what the reference's exporters and audit scripts read -- are taken from the source
 text with a brace-depth scanner that survives the four snapshot-truncated scripts (``truncated: true`` marks a literal
-whose tail is missing; the keys up to the cut are kept).  The constant ``"method"`` value is recorded as well.
+whose tail is missing; the keys up to the cut are kept).  The constant ``"method"`` value is recorded as well, and the keys of
+the per-video ``result`` record each main loop appends to ``checkpoint.json`` / ``summary.json``.
 """
 from __future__ import annotations
 
@@ -86,8 +87,11 @@ def main():
         summary, cut = dict_keys(src, "    summary = {")
         config, _ = dict_keys(src, "    exp_config = {")
         m = re.search(r'    summary = \{\s*"method": "([^"]+)"', src)
+        at = re.search(r"\n +result = \{", src)          # the per-video record of the main loop
+        result, _ = dict_keys(src[at.start():], "result = {")
         table[method] = {"summary_keys": list(summary), "summary_truncated": cut, "summary_method": m.group(1),
-                         "config": config}
+                         "config": config, "result_keys": list(result),
+                         "result_keys_later": sorted(set(re.findall(r'result\["([a-z_0-9]+)"\]\s*=', src)))}
         print(method, len(summary), "summary keys", "(truncated)" if cut else "", "| config:", list(config) if config else None)
     path = ROOT / "tests" / "golden" / "output_layout.json"
     path.write_text(json.dumps(table, indent=1) + "\n")

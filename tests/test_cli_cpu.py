@@ -220,3 +220,23 @@ def test_output_files_carry_the_reference_keys(golden_dir, method):
         cfg = cli.experiment_config(method, args, adapter, {"total": 2})
         _covers(cfg, layout["config"])
         assert cfg["method"] == "lora_tta_builtin" and cfg["clip_gate"]["sampling_mode"] == "late_only"
+
+
+@pytest.mark.parametrize("method,loop_out", [
+    ("lora", {}), ("delta_a", {"delta_norm": 0.1}), ("delta_b", {"delta_norms": [0.1, 0.2]}),
+    ("delta_c", {"delta_out_norm": 0.1, "delta_out_values": [0.0] * 16}), ("norm_tune", {}), ("film", {"correction_norm": 0.3}),
+])
+def test_per_video_record_carries_the_reference_keys(golden_dir, method, loop_out):
+    """The record appended per video = run()'s identification fields + training_record(...) + total_time; it holds every
+    key of the reference's ``result`` literal for the method (generation outputs gen_time / output_path excepted: they
+    only exist when a video is generated, there as here)."""
+    import json
+    layout = json.loads((golden_dir / "output_layout.json").read_text())[method]
+    args = cli.build_parser(method).parse_args(["--output-dir", "/tmp/x"])
+    r = {"losses": [1.0, 0.5], "train_time": 2.0, "es_check_time": 0.5, "early_stopping_info": {"total_checks": 2}, **loop_out}
+    rec = {"idx": 0, "video_name": "v", "video_path": "", "caption": "c", "batch_size": 1, "num_neighbors": 0,
+           **cli.training_record(method, args, r), "total_time": 3.0}
+    want = set(layout["result_keys"]) | (set(layout["result_keys_later"]) - {"gen_time", "output_path"})
+    assert want <= set(rec), want - set(rec)
+    assert rec["final_loss"] == 0.5 and rec["num_train_steps"] == 2 and rec["success"] is True
+    assert cli.training_record(method, args, {**r, "losses": []})["final_loss"] is None
