@@ -21,10 +21,9 @@ What is saved where (HBM layout, N tokens, C hidden, F ffn):
 """
 from __future__ import annotations
 
-import math
 import os
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn

@@ -10,12 +10,12 @@ all-reduced once per step with NCCL; the 1/world scale is folded into the clip /
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional
 
 import torch
 
 from . import ops
-from .engine import Extras, Geometry, TTAEngine
+from .engine import Geometry, TTAEngine
 
 BF16, F32 = torch.bfloat16, torch.float32
 

@@ -20,7 +20,6 @@ import io
 import json
 import os
 import subprocess
-import sys
 import tempfile
 from pathlib import Path
 
