@@ -329,14 +329,27 @@ def run_b200(args):
         "achieved_tflops_per_gpu": tflops,
         "frac_of_nominal_2250": tflops / 2250.0,
         "frac_of_measured_sustained": tflops / peaks["tflops_sustained"],
-        "kernel_ms_per_step": {k: {"ms": round(v["ms"], 3), "n": v["n"],
-                                   "tflops": (round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None)}
-                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "kernel_ms_per_step": kernel_table(prof, peaks),
         "loss_first_last": [loss_vals[0], loss_vals[-1]],
     }
     print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_table(prof, peaks):
+    """Per kernel family of one profiled step: CUDA-event time, launches, algorithmic TFLOP/s and -- the second half of
+    BASELINE.json's metric, "attn/GEMM tensor-pipe % of peak" -- that rate as a fraction of the nominal 2 250 TFLOP/s and
+    of the measured sustained cuBLAS figure (None for the HBM-bound families, which carry no FLOP count)."""
+    table = {}
+    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        row = {"ms": round(v["ms"], 3), "n": v["n"], "tflops": None}
+        if v["flops"] and v["ms"] > 0:
+            t = v["flops"] / (v["ms"] / 1e3) / 1e12
+            row.update({"tflops": round(t, 1), "frac_of_nominal_2250": round(t / 2250.0, 4),
+                        "frac_of_measured_sustained": round(t / peaks["tflops_sustained"], 4)})
+        table[k] = row
+    return table
 
 
 def _call_flops(name, a):

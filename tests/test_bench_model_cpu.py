@@ -42,3 +42,17 @@ def test_config0_cpu_leg_runs_the_oracle_loop():
     r = bench.cpu_tiny_sample(2, steps=2, warmup=0)
     assert r["kind"] == "port" and r["cores"] == 2 and r["unit"] == bench.UNIT and r["value"] > 0
     assert "configs[0]" in r["sample"] and "2 timed steps" in r["sample"]
+
+
+def test_kernel_table_reports_tensor_pipe_fractions():
+    import bench
+    prof = {"attn_bwd[self]": {"ms": 2678.634, "n": 48, "flops": 48 * 49.441406976e12},
+            "ln_mod_fwd": {"ms": 46.8, "n": 265, "flops": 0}, "gemm": {"ms": 216.469, "n": 53, "flops": 3.2421e14}}
+    t = bench.kernel_table(prof, {"tflops_sustained": 1399.5})
+    assert list(t) == ["attn_bwd[self]", "gemm", "ln_mod_fwd"]                       # by time, descending
+    a = t["attn_bwd[self]"]
+    assert a["tflops"] == 886.0 and a["frac_of_nominal_2250"] == round(885.97 / 2250, 4)
+    assert abs(a["frac_of_measured_sustained"] - 0.6331) < 1e-3
+    assert t["ln_mod_fwd"] == {"ms": 46.8, "n": 265, "tflops": None}
+    import json
+    json.dumps(t)
