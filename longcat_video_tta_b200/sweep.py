@@ -12,6 +12,7 @@ resulting command lines are the contract; SLURM itself is not rebuilt.  Here the
 from __future__ import annotations
 
 import os
+import shlex
 import subprocess
 import sys
 from pathlib import Path
@@ -197,17 +198,17 @@ def run_rows(commands: Sequence[Tuple[str, str, List[str]]], gpus: int = 1, pyth
     while nxt < len(commands) or running:
         while nxt < len(commands) and len(running) < max(1, gpus):
             run_id, script, argv = commands[nxt]
-            gpu = next(g for g in range(max(1, gpus)) if g not in running)
+            gpu = nxt % max(1, gpus) if dry_run else next(g for g in range(max(1, gpus)) if g not in running)
             cmd = [python, str(root / script), *argv]
             if dry_run:
-                print(f"  [DRY-RUN] CUDA_VISIBLE_DEVICES={gpu} {' '.join(cmd)}")
+                print(f"  [DRY-RUN] CUDA_VISIBLE_DEVICES={gpu} {shlex.join(cmd)}")
                 done[nxt] = {"run_id": run_id, "returncode": None}
             else:
                 if not (root / script).is_file():
                     raise NotImplementedError(f"{script} is not part of this build (full-model TTA is out of scope)")
                 env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(gpu)) if gpus > 1 else None
                 log = open(log_dir / f"{run_id}.log", "w") if log_dir else None
-                print(f"  Starting {run_id} on GPU {gpu}: {' '.join(cmd)}")
+                print(f"  Starting {run_id} on GPU {gpu}: {shlex.join(cmd)}")
                 running[gpu] = (nxt, subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT if log else None))
             nxt += 1
         for gpu, (i, proc) in list(running.items()):
