@@ -168,7 +168,10 @@ int b200tta_attn_bsa_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* d
  * Replace the unfused ATen chains of the upstream block.
  * ---------------------------------------------------------------------------------- */
 
-/* y = LN(x) * (mul_base + scale[f]) + shift[f]   (eps 1e-6, fp32 math, bf16 in/out)
+/* Replaces: the LayerNorm + AdaLN-modulate chains of the upstream block, whose inputs the reference exposes at
+ * delta_experiment/scripts/run_delta_a.py:196-207 (block call with the per-frame timestep embedding t), run_film_tta.py:129-144
+ * (hook on adaLN_modulation's output) and run_norm_tune_tta.py:78-96 (pre_crs_attn_norm weight / bias as trainables).
+ * y = LN(x) * (mul_base + scale[f]) + shift[f]   (eps 1e-6, fp32 math, bf16 in/out)
  * modulated form: scale/shift f32 rows of the adaLN output, f = row / tokens_per_frame, mul_base = 1
  * affine form (pre_crs_attn_norm): scale = weight, shift = bias (bf16, params_bf16 = 1), mod_ld = 0, mul_base = 0 */
 int b200tta_ln_mod_fwd(void* Y, int64_t ldy, const void* X, int64_t ldx, const void* scale, const void* shift,
@@ -181,7 +184,9 @@ int b200tta_ln_mod_bwd(void* dX, int64_t lddx, const void* dX_resid, int64_t ldr
                        float mul_base, float* dscale_acc, float* dshift_acc, int64_t acc_ld, int64_t rows, int32_t C,
                        int32_t tokens_per_frame, float eps, b200tta_stream_t stream);
 
-/* per-head RMSNorm(128) * weight then 3-D RoPE (interleaved pairs; axis dims 44/42/42 for D=128).
+/* Replaces: q_norm / k_norm (RMSNorm over head_dim; their weights are the qk_norm trainables of
+ * run_norm_tune_tta.py:85-96) followed by the upstream 3-D rotary embedding.
+ * per-head RMSNorm(128) * weight then 3-D RoPE (interleaved pairs; axis dims 44/42/42 for D=128).
  * X [rows, n_slots, 128] bf16 with row stride ldx; slots [0, n_q_slots) use wq, [n_q_slots, n_q_slots+n_k_slots) use wk.
  * rope = 0 skips the rotation (cross-attention).  grid (T, Hh, Ww): row -> (t, h, w) row-major with row_offset. */
 int b200tta_qk_rmsnorm_rope_fwd(void* Y, int64_t ldy, const void* X, int64_t ldx, const void* wq, const void* wk,
@@ -193,13 +198,16 @@ int b200tta_qk_rmsnorm_rope_bwd(void* dX, int64_t lddx, const void* dY, int64_t 
                                 int32_t n_k_slots, int64_t rows, int64_t row_offset, int32_t grid_h, int32_t grid_w,
                                 int32_t rope, float rope_base, float eps, b200tta_stream_t stream);
 
-/* dY = bf16(gate[f] * dX) (backward of x + gate * branch wrt branch); gate NULL -> copy.
+/* Replaces: autograd through the gated residual x + gate * branch of the upstream block (the gate is a chunk of the
+ * adaLN output that FiLM corrects, run_film_tta.py:129-144); the forward gate-residual is a GEMM epilogue.
+ * dY = bf16(gate[f] * dX) (backward of x + gate * branch wrt branch); gate NULL -> copy.
  * optional dgate_acc[f, c] += sum_rows dX * branch (branch bf16, needed by FiLM / delta adapters). */
 int b200tta_gate_mul(void* dY, int64_t lddy, const void* dX, int64_t lddx, const float* gate, int64_t ldg,
                      const void* branch, int64_t ldb, float* dgate_acc, int64_t acc_ld, int64_t rows, int32_t C,
                      int32_t tokens_per_frame, b200tta_stream_t stream);
 
-/* Noising + concat + patchify (common.py:458-470 fused with PatchEmbed3D's im2col):
+/* Noising + concat + patchify (delta_experiment/scripts/common.py:458-470 fused with the im2col of PatchEmbed3D,
+ * x_embedder call at run_delta_a.py:154):
  *   P[n, c*4 + ph*2 + pw] = bf16(cond) for context frames, bf16((1-sigma) x0 + sigma eps) for target frames
  *   V[n_tgt, (ph*2+pw)*16 + c] = f32(bf16(eps - x0))   velocity target in final-layer column order
  *   timestep[t] = 0 | f32(bf16(sigma * 1000))
@@ -207,38 +215,44 @@ int b200tta_gate_mul(void* dY, int64_t lddy, const void* dX, int64_t lddx, const
 int b200tta_noise_patchify(void* P, float* V, float* timestep, const void* cond, const void* target, const void* noise,
                            const float* sigma, int32_t t_cond, int32_t t_tgt, int32_t H, int32_t W,
                            float num_train_timesteps, b200tta_stream_t stream);
-/* plain patchify of a [16,T,H,W] bf16 latent (forward-only API) */
+/* plain patchify of a [16,T,H,W] bf16 latent (forward-only API; x_embedder, run_delta_a.py:154) */
 int b200tta_patchify(void* P, const void* latent, int32_t T, int32_t H, int32_t W, b200tta_stream_t stream);
-/* tokens [T*H/2*W/2, 64] f32 (final-layer order) -> latent [16,T,H,W] f32 */
+/* tokens [T*H/2*W/2, 64] f32 (final-layer order) -> latent [16,T,H,W] f32   (dit.unpatchify, run_delta_a.py:214) */
 int b200tta_unpatchify(float* latent, const float* tokens, int32_t T, int32_t H, int32_t W, b200tta_stream_t stream);
 
-/* d(pred): latent-layout f32 gradient [16,T,H,W] -> token-layout bf16 [(T - t_begin)*H/2*W/2, 64] (frames >= t_begin) */
+/* autograd through unpatchify (loss.backward(), run_lora_tta.py:512).
+ * d(pred): latent-layout f32 gradient [16,T,H,W] -> token-layout bf16 [(T - t_begin)*H/2*W/2, 64] (frames >= t_begin) */
 int b200tta_latent_to_tokens(void* tokens, const float* latent, int32_t T, int32_t H, int32_t W, int32_t t_begin,
                              b200tta_stream_t stream);
 
-/* standalone SwiGLU (used when w1/w3 carry LoRA adapters and cannot be co-tiled): h = silu(h1) * h3 over n bf16
+/* Replaces: silu(w1 x) * w3 x of the upstream FeedForward (ffn.w1 / w2 / w3, run_lora_tta.py:163-168).
+ * standalone SwiGLU (used when w1/w3 carry LoRA adapters and cannot be co-tiled): h = silu(h1) * h3 over n bf16
  * elements, and its backward (dh1, dh3) from dh. */
 int b200tta_swiglu_fwd(void* Hout, const void* H1, const void* H3, int64_t n, b200tta_stream_t stream);
 int b200tta_swiglu_bwd(void* dH1, void* dH3, const void* dH, const void* H1, const void* H3, int64_t n,
                        b200tta_stream_t stream);
 
-/* loss += mean((pred - V)^2) over n elements; dpred = bf16(2 (pred - V) / n * loss_scale). loss must be zeroed. */
+/* Replaces: F.mse_loss and its backward (delta_experiment/scripts/common.py:485-488; run_lora_tta.py:512).
+ * loss += mean((pred - V)^2) over n elements; dpred = bf16(2 (pred - V) / n * loss_scale). loss must be zeroed. */
 int b200tta_mse_fwd_bwd(float* loss, void* dpred, const float* pred, const float* V, int64_t n, float loss_scale,
                         b200tta_stream_t stream);
 
-/* sinusoidal timestep features: F[t, :] = cat(cos(t w_i), sin(t w_i)), i < dim/2 (f32) */
+/* Replaces: t_embedder's frequency embedding (called at run_delta_a.py:163-165).
+ * sinusoidal timestep features: F[t, :] = cat(cos(t w_i), sin(t w_i)), i < dim/2 (f32) */
 int b200tta_timestep_sinusoid(float* F, const float* timestep, int32_t rows, int32_t dim, b200tta_stream_t stream);
 /* small-M fp32 linear with bf16/f32 weights: Y[R,out] = act(X[R,in]) W^T + b (+ addend); act: 0 none, 1 SiLU on input.
  * Used for t_embedder and adaLN_modulation (fp32 islands); R <= 64. */
 int b200tta_skinny_linear(float* Y, const float* X, const void* W, const void* bias, const float* addend,
                           int32_t w_bf16, int32_t R, int32_t in_features, int32_t out_features, int32_t act,
                           b200tta_stream_t stream);
-/* backward wrt the input: dX[R,in] = (dY[R,out] W) * act'(X) ; accumulate = 1 adds into dX */
+/* backward wrt the input: dX[R,in] = (dY[R,out] W) * act'(X) ; accumulate = 1 adds into dX.  This is the path the delta-A / delta-B
+ * gradient takes back to the timestep embedding (offset added at run_delta_a.py:168, run_delta_b.py:194-211). */
 int b200tta_skinny_linear_bwd(float* dX, const float* dY, const float* X, const void* W, int32_t w_bf16, int32_t R,
                               int32_t in_features, int32_t out_features, int32_t act, int32_t accumulate,
                               b200tta_stream_t stream);
 
-/* LoRA side products (token-dimension reductions), bf16 in, fp32 accumulate:
+/* LoRA side products (token-dimension reductions), bf16 in, fp32 accumulate: lora_down(x) of LoRALinear.forward
+ * (run_lora_tta.py:258) and the autograd products that give lora_down / lora_up their .grad (run_lora_tta.py:512):
  *   down:  T[n_tok, r] = bf16(scale * X[n_tok, k] * Wd^T)   Wd [r, k]      (wd_t = 0)
  *                      = bf16(scale * X[n_tok, k] * Wd)     Wd [k, r]      (wd_t = 1)
  *   grad:  G[m, r] (f32) += P[n_tok, m]^T * Q[n_tok, r] */
