@@ -25,6 +25,7 @@ from typing import Dict, List
 import torch
 
 from . import adapters as A
+from . import dist as D
 from . import lora as L
 from .common import split_tta_latents
 from .dit import B200DiT
@@ -250,6 +251,15 @@ def run(method: str, argv=None) -> Dict:
     out.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(args.seed)
     device = args.device
+    # Under torchrun the step runs data-parallel over noise draws (dist.py): one process per GPU, every rank
+    # the same videos and adapters, its own (sigma, eps) stream, gradients all-reduced inside TTAStepper; rank 0 alone
+    # writes the output files.  Without torchrun: world = 1 and nothing below differs from the single-GPU run.
+    world = D.init_from_env()
+    rank = D.rank()
+    if world > 1 and str(device).startswith("cuda"):
+        device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
+        torch.cuda.set_device(device)
+    save_json = _save_json if rank == 0 else (lambda path, obj: None)
     try:
         import longcat_video  # noqa: F401  (upstream package: VAE / text encoder / pipeline)
         have_upstream = True
@@ -318,7 +328,7 @@ def run(method: str, argv=None) -> Dict:
         adapter_cfg = {method: {k: v for k, v in vars(args).items() if k.startswith(("delta", "norm", "film", "num_groups"))},
                        "trainable_params": n_train}
 
-    _save_json(out / "config.json", experiment_config(method, args, adapter_cfg, {
+    save_json(out / "config.json", experiment_config(method, args, adapter_cfg, {
         "total": total, "context": ctx, "latent_frames": n_lat, "context_latents": n_ctx_lat}))
     ckpt_path = out / "checkpoint.json"
     state = {"next_idx": 0, "results": []}
@@ -335,6 +345,8 @@ def run(method: str, argv=None) -> Dict:
         try:
             cond, train, val = split_tta_latents(vid["latents"], n_ctx_lat, args.es_holdout_fraction)
             model = dit if method == "lora" else wrapper
+            if world > 1:       # replicas re-initialise identically ...
+                torch.manual_seed(args.seed + 1_000_003 * (idx + 1))
             # reset the adapter for every video (run_lora_tta.py:1127)
             if method == "lora":
                 (L.reset_builtin_lora_weights if args.use_builtin_lora else L.reset_lora_weights)(mods)
@@ -344,6 +356,8 @@ def run(method: str, argv=None) -> Dict:
             else:
                 for p in wrapper.trainable():
                     p.data.zero_()
+            if world > 1:       # ... and then draw from their own stream (world = 1 keeps the reference's single stream)
+                torch.manual_seed(D.draw_seed(args.seed + 1_000_003 * (idx + 1) + 7919, rank))
             es = early_stopper if (early_stopper is not None and val is not None) else None
             if es is not None:
                 save_fn = (lambda: [p.data.clone() for p in (L.get_lora_parameters(mods) if method == "lora" else wrapper.trainable())])
@@ -373,7 +387,7 @@ def run(method: str, argv=None) -> Dict:
                                                     warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
                                                     max_grad_norm=args.max_grad_norm, device=device, dtype=BF16,
                                                     early_stopper=es, train_latents_variants=variants)
-                if args.save_lora_weights and not args.use_builtin_lora:
+                if args.save_lora_weights and not args.use_builtin_lora and rank == 0:
                     (out / "lora_weights").mkdir(exist_ok=True)
                     L.save_lora_weights(mods, str(out / "lora_weights" / f"{vid['video_name']}_lora.pt"))
             else:
@@ -392,12 +406,16 @@ def run(method: str, argv=None) -> Dict:
                 r.setdefault("es_check_time", 0.0)
             result.update(training_record(method, args, r))
         except Exception as e:  # per-video failure is recorded and the run continues (run_lora_tta.py:1264-1271)
+            if world > 1:       # ... unless other ranks are waiting in a collective: fail the whole job loudly
+                raise
             result.update({"success": False, "error": f"{type(e).__name__}: {e}"})
         result["total_time"] = time.time() - t_video
         state["results"].append(result)
         state["next_idx"] = idx + 1
-        _save_json(ckpt_path, state)
+        save_json(ckpt_path, state)
 
     summary = summary_record(method, args, state["results"])
-    _save_json(out / "summary.json", summary)
+    save_json(out / "summary.json", summary)
+    if world > 1:
+        torch.distributed.barrier()
     return summary

@@ -45,6 +45,19 @@ def draw_seed(base_seed: int, rank_: int) -> int:
     return int(base_seed) + int(rank_)
 
 
+def rank0_value(value: float, device="cpu", group=None) -> float:
+    """Rank 0's value of a host-side scalar that feeds a control decision (the early stopper's anchor loss): replicas
+    hold identical adapters, but the kernels' summation order is timing dependent, so two ranks may see anchor losses
+    that differ in the last bits -- one would stop and the others would wait in the next all-reduce.  One 8-byte
+    broadcast per check keeps every rank on rank 0's decision."""
+    if world_size(group) == 1:
+        return value
+    dev = device if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return float(t.item())
+
+
 def all_reduce_grads(buffers: Iterable[torch.Tensor], group=None) -> float:
     """Sum the gradient buffers over the ranks in place; returns the factor (1 / world) the optimizer kernels must
     apply to turn the sum into the mean over draws."""

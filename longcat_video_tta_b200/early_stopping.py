@@ -10,6 +10,7 @@ from typing import Callable, List, Optional, Tuple
 import torch
 
 from .common import compute_flow_matching_loss_conditioned_fixed
+from .dist import rank0_value
 
 BF16 = torch.bfloat16
 
@@ -118,4 +119,4 @@ class AnchoredEarlyStopper:
             fixed_noises=self.fixed_noises, device=self.device, dtype=self.dtype, forward_fn=self.forward_fn)
         if was_training:
             self.model.train()
-        return loss
+        return rank0_value(loss, self.device)        # identity outside a data-parallel run

@@ -69,3 +69,67 @@ def test_two_rank_gradient_mean_and_identical_updates():
         assert torch.allclose(a, b, rtol=0, atol=1e-7)
     # world = 1 degenerates to the single-GPU run (same seed, no collective, scale 1)
     assert D.draw_seed(42, 0) == 42 and D.all_reduce_grads([torch.ones(3)]) == 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The method scripts under torchrun: host control flow of cli.run with the GPU pieces replaced by recorders, and the
+# early stopper's decision input agreed across ranks.
+def _script_worker(rank, world, port, out, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import types
+    from longcat_video_tta_b200 import cli, early_stopping
+    cfg = types.SimpleNamespace(caption_channels=32, adaln_tembed_dim=512, hidden_size=64, out_channels=16)
+    dit = types.SimpleNamespace(config=cfg, engine=types.SimpleNamespace(resolve_sites=lambda: None), training=False,
+                                eval=lambda: None, train=lambda: None)
+    seen = {"init": [], "draw": [], "anchor": []}
+    cli.B200DiT.random_init = staticmethod(lambda *a, **k: dit)
+    cli.L.inject_lora_into_dit = lambda d, **kw: ["m0"]
+    cli.L.count_lora_parameters = lambda mods: {"trainable": 1}
+    cli.L.get_lora_parameters = lambda mods: []
+    cli.L.reset_lora_weights = lambda mods: seen["init"].append(float(torch.rand(1)))     # stands for the kaiming re-init
+
+    def loop(d, mods, cond, train, pe, pm, early_stopper=None, **kw):
+        seen["draw"].append(float(torch.rand(1)))                                         # stands for (sigma, eps)
+        stops = []
+        for step in range(1, 5):
+            stop, info = early_stopper.step(step, save_fn=lambda: step)
+            stops.append(stop)
+            if stop:
+                break
+        early_stopper.restore(restore_fn=lambda s: None)
+        return {"losses": [1.0] * len(stops), "train_time": 0.0, "es_check_time": 0.0,
+                "early_stopping_info": early_stopper.state}
+
+    cli.L.finetune_lora_on_conditioning = loop
+    # anchor losses that differ between the ranks in the last digits, around the "improved" threshold
+    series = iter([1.0, 0.9, 0.9 + (1e-9 if rank else -1e-9), 0.9 + (-2e-9 if rank else 2e-9), 0.95, 0.96] * 4)
+
+    def anchor(**kw):
+        v = next(series)
+        seen["anchor"].append(v)
+        return v
+
+    early_stopping.compute_flow_matching_loss_conditioned_fixed = anchor
+    s = cli.run("lora", (f"--output-dir {out_dir} --synthetic --model tiny --device cpu --latent-hw 8,8 --tta-total-frames 17 "
+                         f"--tta-context-frames 5 --max-videos 2 --es-check-every 1 --es-patience 2 --num-steps 4").split())
+    out[rank] = dict(seen=seen, results=s["results"])
+    dist.destroy_process_group()
+
+
+def test_scripts_under_torchrun_host_flow(tmp_path):
+    import json
+    world, port = 2, _free_port()
+    out = mp.Manager().dict()
+    mp.spawn(_script_worker, args=(world, port, out, str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    assert r0["seen"]["init"] == r1["seen"]["init"] and len(r0["seen"]["init"]) == 2     # identical re-initialisation
+    assert all(a != b for a, b in zip(r0["seen"]["draw"], r1["seen"]["draw"]))             # own draw stream per rank
+    assert r0["seen"]["anchor"] != r1["seen"]["anchor"]                                    # ranks did see different bits
+    for a, b in zip(r0["results"], r1["results"]):                                         # ... and decided alike
+        assert a["early_stopping_info"] == b["early_stopping_info"] and a["num_train_steps"] == b["num_train_steps"]
+    h = r0["results"][0]["early_stopping_info"]["loss_history"]
+    assert [v for _, v in h] == r0["seen"]["anchor"][:len(h)]                              # rank 0's values rule
+    # rank 0 alone wrote the files, once
+    ck = json.loads((tmp_path / "checkpoint.json").read_text())
+    assert ck["next_idx"] == 2 and len(ck["results"]) == 2
+    assert (tmp_path / "summary.json").exists() and (tmp_path / "config.json").exists()
