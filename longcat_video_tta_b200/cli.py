@@ -27,7 +27,7 @@ import torch
 from . import adapters as A
 from . import dist as D
 from . import lora as L
-from .common import split_tta_latents
+from .common import resolve_tta_frames, split_tta_latents, validate_tta_feature_budget
 from .dit import B200DiT
 from .early_stopping import add_early_stopping_args, build_early_stopper_from_args
 
@@ -219,11 +219,12 @@ def training_record(method: str, args, r: Dict) -> Dict:
     return rec
 
 
-def frame_budget(args):
-    """run_lora_tta.py:743-758: latent frames used for TTA and the context split."""
-    total = args.tta_total_frames or args.num_cond_frames
-    ctx = args.tta_context_frames or total
-    ctx = min(ctx, total)
+def frame_budget(args, context: str = ""):
+    """Resolved TTA window (run_lora_tta.py:743-758, guard included) and what it is in latent frames: the VAE keeps the
+    first pixel frame and then one latent per 4 (run_lora_tta.py:1088-1093)."""
+    resolve_tta_frames(args)
+    validate_tta_feature_budget(args, context=context)
+    total, ctx = args.tta_total_frames, args.tta_context_frames
     n_lat = 1 + (total - 1) // 4
     n_ctx_lat = 1 + (ctx - 1) // 4
     return total, ctx, n_lat, n_ctx_lat
@@ -282,10 +283,10 @@ def run(method: str, argv=None) -> Dict:
         raise NotImplementedError("--batch-videos > 1 is built for the LoRA loop only (finetune_lora_batch); the "
                                   "reference's delta-A batch variant needs the retrieval pool, which is outside the step")
 
+    total, ctx, n_lat, n_ctx_lat = frame_budget(args, context="lora_tta" if method == "lora" else method)
     dit = B200DiT.random_init(args.model, seed=0, device=device)
     cfg = dit.config
     hw = tuple(int(x) for x in args.latent_hw.split(",")) if args.latent_hw else (60, 104)
-    total, ctx, n_lat, n_ctx_lat = frame_budget(args)
 
     # ---- adapters
     mods = wrapper = norm_params = None

@@ -64,6 +64,65 @@ def estimate_tta_split_budget(tta_total_frames: int, tta_context_frames: int, ho
             "val_latents": int(t_val)}
 
 
+def resolve_tta_frames(args) -> None:
+    """The block every method script runs after parsing (run_lora_tta.py:743-757): the TTA window defaults to the
+    conditioning frames, a missing or too large context does too, and the window never reaches past
+    ``gen_start_frame`` (no ground-truth leakage).  Resolves ``args.tta_total_frames`` / ``args.tta_context_frames``
+    in place."""
+    if args.tta_total_frames is None:
+        args.tta_total_frames = args.num_cond_frames
+    if args.tta_context_frames is None or args.tta_context_frames > args.tta_total_frames:
+        args.tta_context_frames = args.num_cond_frames
+    if args.tta_total_frames > args.gen_start_frame:
+        print(f"[WARN] tta_total_frames ({args.tta_total_frames}) exceeds gen_start_frame ({args.gen_start_frame}); "
+              f"clamping to avoid GT leakage.")
+        args.tta_total_frames = args.gen_start_frame
+    args.tta_context_frames = min(args.tta_context_frames, args.tta_total_frames)
+
+
+def validate_tta_feature_budget(args, context: str = "") -> Dict:
+    """Does the resolved frame budget leave room for what is switched on (common.py:1520-1598)?  Early stopping needs at
+    least one held-out latent frame; the CLIP gate (recorded only in this build, checked all the same so that a sweep
+    fails where the reference's would) needs enough candidate frames.  ``feature_frame_guard_mode``: fail | warn | off."""
+    mode = str(getattr(args, "feature_frame_guard_mode", "fail")).lower()
+    mode = mode if mode in ("fail", "warn", "off") else "fail"
+    tag = f"[feature_budget:{context}]" if context else "[feature_budget]"
+    total = int(getattr(args, "tta_total_frames", 0) or 0)
+    ctx = int(getattr(args, "tta_context_frames", 0) or 0)
+    holdout = float(getattr(args, "es_holdout_fraction", 0.25) or 0.25)
+    split = estimate_tta_split_budget(total, ctx, holdout_fraction=holdout)
+    info: Dict = {"split_budget": split}
+    issues = []
+    if not getattr(args, "es_disable", False) and split["val_latents"] < 1:
+        issues.append(f"ES is enabled but estimated val_latents=0 (tta_total_frames={total}, tta_context_frames={ctx}, "
+                      f"holdout={holdout}). Increase tta_total_frames and/or reduce tta_context_frames.")
+    if getattr(args, "clip_gate_enabled", False):
+        sampling = "late_only" if getattr(args, "clip_gate_late_only", False) else \
+            str(getattr(args, "clip_gate_sampling_mode", "full_window"))
+        late = float(getattr(args, "clip_gate_late_fraction", 0.4) or 0.4)
+        backend = str(getattr(args, "clip_gate_backend", "clip") or "clip").lower()
+        need = 8 if backend == "xclip" else int(getattr(args, "clip_gate_sample_frames", 4) or 4)
+        window = max(1, total)
+        have = max(1, int(round(window * min(max(late, 1e-6), 1.0)))) if (sampling or "full_window").lower() == "late_only" \
+            else window
+        info.update(clip_candidates=int(have), clip_required_frames=int(need))
+        if have < need:
+            issues.append(f"CLIP gate is enabled but candidate frames are fewer than required (candidates={have}, "
+                          f"required={need}, tta_total_frames={total}, sampling_mode={sampling}, late_fraction={late}). "
+                          f"Increase tta_total_frames and/or adjust sampling.")
+    if mode != "off":
+        print(f"{tag} split(total={split['total_latents']}, cond={split['cond_latents']}, train={split['train_latents']}, "
+              f"val={split['val_latents']})")
+        if "clip_candidates" in info:
+            print(f"{tag} clip_candidates={info['clip_candidates']} required={info['clip_required_frames']}")
+    if issues and mode != "off":
+        msg = f"{tag} " + " | ".join(issues)
+        if mode == "fail":
+            raise RuntimeError(msg)
+        print(f"WARNING: {msg}")
+    return info
+
+
 def _draw(target, device, sigma_min, sigma_max):
     B = target.shape[0]
     sigma = torch.rand(B, device=device, dtype=torch.float32) * (sigma_max - sigma_min) + sigma_min

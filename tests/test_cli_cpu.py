@@ -27,13 +27,13 @@ def test_adapter_flags(method, flags):
 
 
 def test_frame_budget_and_split_match_survey_3_1():
-    a = cli.build_parser("lora").parse_args("--output-dir /tmp/x --num-cond-frames 14".split())
+    a = cli.build_parser("lora").parse_args("--output-dir /tmp/x --num-cond-frames 14 --feature-frame-guard-mode warn".split())
     total, ctx, n_lat, n_ctx = cli.frame_budget(a)
     assert (total, ctx, n_lat, n_ctx) == (14, 14, 4, 4)
     import torch
     c, t, v = split_tta_latents(torch.zeros(1, 1, n_lat, 1, 1), n_ctx)
     assert (c.shape[2], t.shape[2], v) == (3, 1, None)      # early stopping silently inactive
-    a = cli.build_parser("lora").parse_args("--output-dir /tmp/x --tta-total-frames 117 --tta-context-frames 13".split())
+    a = cli.build_parser("lora").parse_args("--output-dir /tmp/x --tta-total-frames 117 --tta-context-frames 13 --gen-start-frame 117".split())
     total, ctx, n_lat, n_ctx = cli.frame_budget(a)
     c, t, v = split_tta_latents(torch.zeros(1, 1, n_lat, 1, 1), n_ctx)
     assert (n_lat, n_ctx) == (30, 4) and (c.shape[2], t.shape[2], v.shape[2]) == (4, 20, 6)
@@ -240,3 +240,33 @@ def test_per_video_record_carries_the_reference_keys(golden_dir, method, loop_ou
     assert want <= set(rec), want - set(rec)
     assert rec["final_loss"] == 0.5 and rec["num_train_steps"] == 2 and rec["success"] is True
     assert cli.training_record(method, args, {**r, "losses": []})["final_loss"] is None
+
+
+def test_frame_budget_resolution_and_guard_match_reference_golden(golden_dir, capsys):
+    """resolve_tta_frames + validate_tta_feature_budget against the reference's own post-parse block and guard, executed
+    by oracle/make_golden_frame_budget.py over 8 400 settings: resolved window, returned info, printed lines, error text."""
+    import argparse
+    import gzip
+    import json
+    from longcat_video_tta_b200.common import resolve_tta_frames, validate_tta_feature_budget
+    rows = json.loads(gzip.open(golden_dir / "frame_budget.json.gz").read())
+    assert len(rows) == 8400 and sum(r["error"] is not None for r in rows) > 1000
+    for r in rows:
+        args = argparse.Namespace(**r["given"])
+        capsys.readouterr()
+        info = err = None
+        try:
+            resolve_tta_frames(args)
+            info = validate_tta_feature_budget(args, context="lora_tta")
+        except RuntimeError as e:
+            err = str(e)
+        assert (args.tta_total_frames, args.tta_context_frames) == (r["total"], r["context"]), r["given"]
+        assert info == r["info"] and err == r["error"], r["given"]
+        assert capsys.readouterr().out.splitlines() == r["printed"], r["given"]
+
+
+def test_default_frames_with_early_stopping_are_refused_like_the_reference(tmp_path):
+    """The reference's own defaults (2 conditioning frames = 1 latent frame, early stopping on) leave no held-out frame:
+    its guard stops the run before the model is loaded, and so does ours."""
+    with pytest.raises(RuntimeError, match="ES is enabled but estimated val_latents=0"):
+        cli.run("lora", f"--output-dir {tmp_path} --synthetic --model tiny --device cpu".split())

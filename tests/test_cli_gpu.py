@@ -33,7 +33,8 @@ def test_run_lora_tta_script_outputs(tmp_path):
     assert set(w) == {f"lora_{i}.{k}" for i in range(10) for k in ("down", "up")}
     assert w["lora_0.down"].shape == (16, 512) and w["lora_0.up"].shape == (1536, 16)
     # resume: nothing left to do
-    again = cli.run("lora", f"--output-dir {out} --synthetic --model tiny --latent-hw 32,32 --max-videos 2".split())
+    again = cli.run("lora", f"--output-dir {out} --synthetic --model tiny --latent-hw 32,32 --tta-total-frames 17 "
+                            "--tta-context-frames 5 --max-videos 2".split())
     assert again["num_videos"] == 2
 
 
