@@ -393,6 +393,27 @@ def optimize_delta_a(wrapper: DeltaAWrapper, cond_latents, train_latents, prompt
             "early_stopping_info": es}
 
 
+def _optimize_delta_a_batch(wrapper: DeltaAWrapper, batch_data: List[Dict], num_steps: int = 20, lr: float = 1e-3,
+                            device: str = "cuda", dtype: torch.dtype = BF16) -> Dict:
+    """run_delta_a.py:308-362: ONE shared delta vector trained round-robin (``step % K``) over K pre-encoded videos that
+    stay on the host; no variants, no early stopping.  Per step the reference draws sigma, then eps, and nothing else."""
+    stepper = TTAStepper(wrapper.dit, adapter=wrapper, train_lora=False, eps=1e-15, weight_decay=0.01, max_grad_norm=1.0,
+                         per_tensor_clip=wrapper.per_tensor_clip)
+    wrapper.train()
+    losses = []
+    for step in range(num_steps):
+        bd = batch_data[step % len(batch_data)]
+        cond, train = bd["cond_latents"].to(device, non_blocking=True), bd["train_latents"].to(device, non_blocking=True)
+        pe = bd["prompt_embeds"].to(device, non_blocking=True)
+        pm = bd["prompt_mask"].to(device, non_blocking=True) if bd["prompt_mask"] is not None else None
+        sigma = torch.rand(train.shape[0], device=device, dtype=F32) * (1.0 - 0.001) + 0.001
+        noise = torch.randn_like(train)
+        losses.append(stepper.step(cond, train, pe, pm, sigma, noise, lr))
+    losses = [float(v) for v in torch.cat(losses).tolist()] if losses else []
+    return {"losses": losses, "delta_norm": wrapper.delta.detach().norm().item(), "es_check_time": 0.0,
+            "early_stopping_info": None}
+
+
 def optimize_delta_b(wrapper: DeltaBWrapper, cond_latents, train_latents, prompt_embeds, prompt_mask, num_steps: int = 20,
                      lr: float = 1e-3, device: str = "cuda", dtype: torch.dtype = BF16, early_stopper=None,
                      train_latents_variants: Optional[List[Dict]] = None) -> Dict:

@@ -279,9 +279,9 @@ def run(method: str, argv=None) -> Dict:
         raise NotImplementedError("--also-tune-delta (norm parameters + a delta-A vector in one optimizer, "
                                   "run_norm_tune_tta.py:380-390) is not wired into the fused step; run norm_tune and "
                                   "delta_a separately")
-    if args.batch_videos > 1 and method != "lora":
-        raise NotImplementedError("--batch-videos > 1 is built for the LoRA loop only (finetune_lora_batch); the "
-                                  "reference's delta-A batch variant needs the retrieval pool, which is outside the step")
+    if args.batch_videos > 1 and method not in ("lora", "delta_a"):
+        raise NotImplementedError("--batch-videos > 1 exists for LoRA (finetune_lora_batch) and delta-A "
+                                  "(_optimize_delta_a_batch) only, as in the reference")
 
     total, ctx, n_lat, n_ctx_lat = frame_budget(args, context="lora_tta" if method == "lora" else method)
     dit = B200DiT.random_init(args.model, seed=0, device=device)
@@ -359,14 +359,15 @@ def run(method: str, argv=None) -> Dict:
                     p.data.zero_()
             if world > 1:       # ... and then draw from their own stream (world = 1 keeps the reference's single stream)
                 torch.manual_seed(D.draw_seed(args.seed + 1_000_003 * (idx + 1) + 7919, rank))
-            es = early_stopper if (early_stopper is not None and val is not None) else None
+            batch_mode = args.batch_videos > 1      # the reference's batch loops run without the early stopper
+            es = early_stopper if (early_stopper is not None and val is not None and not batch_mode) else None
             if es is not None:
                 save_fn = (lambda: [p.data.clone() for p in (L.get_lora_parameters(mods) if method == "lora" else wrapper.trainable())])
                 es.setup(model, cond, val, vid["prompt_embeds"], vid["prompt_mask"], device=device, dtype=BF16,
                          video_id=vid["video_name"], save_fn=save_fn)
-            if method == "lora" and args.batch_videos > 1:
-                # retrieval-augmented batch (run_lora_tta.py:1037-1062 builds it from the pool; here: the evaluation
-                # video + K-1 further synthetic videos), held on the host and visited round-robin
+            if batch_mode:
+                # retrieval-augmented batch (run_lora_tta.py:1037-1062, run_delta_a.py:~640 build it from the pool; here:
+                # the evaluation video + K-1 further synthetic videos), held on the host and visited round-robin
                 batch = []
                 for j in range(args.batch_videos):
                     nb = vid if j == 0 else synthetic_video(10_000 * j + idx, n_lat, hw, cfg, "cpu")
@@ -374,9 +375,14 @@ def run(method: str, argv=None) -> Dict:
                     batch.append({"cond_latents": c_j.cpu(), "train_latents": t_j.cpu(),
                                   "prompt_embeds": nb["prompt_embeds"].cpu(), "prompt_mask": nb["prompt_mask"].cpu()})
                 result.update({"batch_size": len(batch), "num_neighbors": len(batch) - 1})
+            if batch_mode and method == "lora":
                 r = L.finetune_lora_batch(dit, mods, batch, num_steps=args.num_steps, lr=args.learning_rate,
                                           warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
                                           max_grad_norm=args.max_grad_norm, device=device, dtype=BF16)
+            elif batch_mode:
+                t0 = time.time()
+                r = A._optimize_delta_a_batch(wrapper, batch, num_steps=args.delta_steps, lr=args.delta_lr, device=device)
+                r["train_time"] = time.time() - t0
             elif method == "lora":
                 variants = None
                 if args.aug_enabled and args.aug_flip:
@@ -388,9 +394,6 @@ def run(method: str, argv=None) -> Dict:
                                                     warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
                                                     max_grad_norm=args.max_grad_norm, device=device, dtype=BF16,
                                                     early_stopper=es, train_latents_variants=variants)
-                if args.save_lora_weights and not args.use_builtin_lora and rank == 0:
-                    (out / "lora_weights").mkdir(exist_ok=True)
-                    L.save_lora_weights(mods, str(out / "lora_weights" / f"{vid['video_name']}_lora.pt"))
             else:
                 fn = {"delta_a": A.optimize_delta_a, "delta_b": A.optimize_delta_b, "delta_c": A.optimize_delta_c,
                       "film": A.optimize_film_adapter}.get(method)
@@ -405,6 +408,9 @@ def run(method: str, argv=None) -> Dict:
                            device=device, early_stopper=es)
                 r.setdefault("train_time", time.time() - t0)
                 r.setdefault("es_check_time", 0.0)
+            if method == "lora" and args.save_lora_weights and not args.use_builtin_lora and rank == 0:
+                (out / "lora_weights").mkdir(exist_ok=True)                  # run_lora_tta.py:1250-1252
+                L.save_lora_weights(mods, str(out / "lora_weights" / f"{vid['video_name']}_lora.pt"))
             result.update(training_record(method, args, r))
         except Exception as e:  # per-video failure is recorded and the run continues (run_lora_tta.py:1264-1271)
             if world > 1:       # ... unless other ranks are waiting in a collective: fail the whole job loudly

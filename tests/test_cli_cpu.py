@@ -180,7 +180,8 @@ def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch, golden
     assert calls[-1][3] is None and s["results"][0]["batch_size"] == 1
 
 
-@pytest.mark.parametrize("method,flags", [("norm_tune", "--also-tune-delta"), ("delta_a", "--batch-videos 4")])
+@pytest.mark.parametrize("method,flags", [("norm_tune", "--also-tune-delta"), ("delta_b", "--batch-videos 4"),
+                                          ("film", "--batch-videos 2")])
 def test_unbuilt_combinations_fail_loudly(tmp_path, method, flags):
     with pytest.raises(NotImplementedError):
         cli.run(method, f"--output-dir {tmp_path} --synthetic --model tiny --device cpu {flags}".split())
@@ -270,3 +271,32 @@ def test_default_frames_with_early_stopping_are_refused_like_the_reference(tmp_p
     its guard stops the run before the model is loaded, and so does ours."""
     with pytest.raises(RuntimeError, match="ES is enabled but estimated val_latents=0"):
         cli.run("lora", f"--output-dir {tmp_path} --synthetic --model tiny --device cpu".split())
+
+
+def test_run_delta_a_batch_host_flow(tmp_path, monkeypatch):
+    """--batch-videos K on delta-A: K host-resident videos handed to _optimize_delta_a_batch, no early stopper
+    (run_delta_a.py batch branch), the reference's record fields."""
+    import torch.nn as nn
+    calls = []
+    torch = _stub_engine(monkeypatch, calls)
+
+    class Wrapper:
+        def __init__(self, dit, dim):
+            self.delta = nn.Parameter(torch.zeros(dim))
+
+        def trainable(self):
+            return [self.delta]
+
+    def batch(wrapper, batch_data, **kw):
+        calls.append(("delta_a_batch", batch_data, kw))
+        return {"losses": [0.7] * kw["num_steps"], "delta_norm": 0.25, "es_check_time": 0.0, "early_stopping_info": None}
+
+    monkeypatch.setattr(cli.A, "DeltaAWrapper", Wrapper)
+    monkeypatch.setattr(cli.A, "_optimize_delta_a_batch", batch)
+    s = cli.run("delta_a", (f"--output-dir {tmp_path} --synthetic --model tiny --device cpu --latent-hw 8,8 --tta-total-frames 17 "
+                            f"--tta-context-frames 5 --max-videos 1 --delta-steps 5 --delta-lr 2e-3 --batch-videos 2").split())
+    kind, data, kw = calls[-1]
+    assert kind == "delta_a_batch" and len(data) == 2 and kw["num_steps"] == 5 and kw["lr"] == 2e-3
+    r = s["results"][0]
+    assert r["success"] and (r["batch_size"], r["num_neighbors"], r["delta_norm"], r["num_train_steps"]) == (2, 1, 0.25, 5)
+    assert r["early_stopping_info"] is None and s["method"] == "delta_a" and s["batch_videos"] == 2
