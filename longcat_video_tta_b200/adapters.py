@@ -247,9 +247,13 @@ def restore_params(params, snapshot):
 class NormTuneForward(_AdapterBase):
     """The DiT's own norm affine parameters are the trainables (whichever have requires_grad)."""
 
-    def __init__(self, dit: nn.Module):
+    def __init__(self, dit: nn.Module, also_tune_delta: bool = False, adaln_tembed_dim: int = 512):
+        """``also_tune_delta``: the reference's ``--also-tune-delta`` (run_norm_tune_tta.py:380-390): one fp32 delta-A vector,
+        added to the timestep embedding, joins the norm parameters as the LAST entry of the optimizer's list."""
         nn.Module.__init__(self)
         self.dit = dit   # NOTE: does not re-freeze: the caller has just unfrozen the norm parameters
+        self.delta = nn.Parameter(torch.zeros(adaln_tembed_dim, device=next(dit.parameters()).device)) \
+            if also_tune_delta else None
 
     def _named(self):
         out = []
@@ -260,15 +264,26 @@ class NormTuneForward(_AdapterBase):
         return out
 
     def trainable(self):
-        return [p for _, p in self._named()]
+        return [p for _, p in self._named()] + ([self.delta] if self.delta is not None else [])
 
     def build_extras(self):
         ex = Extras(len(self.dit.blocks))
         ex.norm_grads = True
+        if self.delta is not None:      # as DeltaAWrapper.build_extras: every block and the final layer see t + delta
+            d = self.delta.detach()
+            ex.t_offset = [d] * len(self.dit.blocks)
+            ex.t_offset_final = d
+            ex.need_dmod = ex.need_dt = True
         return ex
 
     def grads_from(self, ex):
-        return [ex.d_norm[k] for k, _ in self._named()]
+        grads = [ex.d_norm[k] for k, _ in self._named()]
+        if self.delta is not None:
+            g = _sum_t(ex.d_t_final)
+            for dt in ex.d_t:
+                g = g + _sum_t(dt)
+            grads.append(g)
+        return grads
 
 
 # ---------------------------------------------------------------------------------------------------- FiLM

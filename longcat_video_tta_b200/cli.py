@@ -275,10 +275,6 @@ def run(method: str, argv=None) -> Dict:
             "common.load_longcat_components / encode_video / encode_prompt, load the DiT weights into B200DiT "
             "(INTEGRATION.md 1a) and call longcat_video_tta_b200.lora.finetune_lora_on_conditioning")
 
-    if getattr(args, "also_tune_delta", False):
-        raise NotImplementedError("--also-tune-delta (norm parameters + a delta-A vector in one optimizer, "
-                                  "run_norm_tune_tta.py:380-390) is not wired into the fused step; run norm_tune and "
-                                  "delta_a separately")
     if args.batch_videos > 1 and method not in ("lora", "delta_a"):
         raise NotImplementedError("--batch-videos > 1 exists for LoRA (finetune_lora_batch) and delta-A "
                                   "(_optimize_delta_a_batch) only, as in the reference")
@@ -320,13 +316,15 @@ def run(method: str, argv=None) -> Dict:
         norm_params = A.collect_norm_params(dit, args.norm_target)
         for p in norm_params:
             p.requires_grad_(True)
-        wrapper = A.NormTuneForward(dit)
+        wrapper = A.NormTuneForward(dit, also_tune_delta=args.also_tune_delta, adaln_tembed_dim=cfg.adaln_tembed_dim)
+        if wrapper.delta is not None:
+            norm_params.append(wrapper.delta)       # run_norm_tune_tta.py:382-385: last in the optimizer's list
     elif method == "film":
         wrapper = A.FiLMAdapterWrapper(dit, num_groups=args.num_groups, hidden_size=cfg.hidden_size, film_mode=args.film_mode)
         wrapper.apply_to_dit()
     if method != "lora":
         n_train = sum(p.numel() for p in wrapper.trainable())
-        adapter_cfg = {method: {k: v for k, v in vars(args).items() if k.startswith(("delta", "norm", "film", "num_groups"))},
+        adapter_cfg = {method: {k: v for k, v in vars(args).items() if k.startswith(("delta", "norm", "film", "num_groups", "also_tune"))},
                        "trainable_params": n_train}
 
     save_json(out / "config.json", experiment_config(method, args, adapter_cfg, {

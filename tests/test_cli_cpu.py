@@ -180,8 +180,7 @@ def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch, golden
     assert calls[-1][3] is None and s["results"][0]["batch_size"] == 1
 
 
-@pytest.mark.parametrize("method,flags", [("norm_tune", "--also-tune-delta"), ("delta_b", "--batch-videos 4"),
-                                          ("film", "--batch-videos 2")])
+@pytest.mark.parametrize("method,flags", [("delta_b", "--batch-videos 4"), ("film", "--batch-videos 2")])
 def test_unbuilt_combinations_fail_loudly(tmp_path, method, flags):
     with pytest.raises(NotImplementedError):
         cli.run(method, f"--output-dir {tmp_path} --synthetic --model tiny --device cpu {flags}".split())
@@ -300,3 +299,39 @@ def test_run_delta_a_batch_host_flow(tmp_path, monkeypatch):
     r = s["results"][0]
     assert r["success"] and (r["batch_size"], r["num_neighbors"], r["delta_norm"], r["num_train_steps"]) == (2, 1, 0.25, 5)
     assert r["early_stopping_info"] is None and s["method"] == "delta_a" and s["batch_videos"] == 2
+
+
+def test_run_norm_tune_with_delta_host_flow(tmp_path, monkeypatch):
+    """--also-tune-delta: the wrapper's delta vector is appended to the list the loop optimises (run_norm_tune_tta.py
+    :382-385), it is part of the per-video reset, and it is counted as trainable."""
+    import json
+    import torch.nn as nn
+    calls = []
+    torch = _stub_engine(monkeypatch, calls)
+    norm = [nn.Parameter(torch.ones(4)), nn.Parameter(torch.ones(4))]
+
+    class Wrapper:
+        def __init__(self, dit, also_tune_delta=False, adaln_tembed_dim=512):
+            self.delta = nn.Parameter(torch.zeros(adaln_tembed_dim)) if also_tune_delta else None
+
+        def trainable(self):
+            return norm + ([self.delta] if self.delta is not None else [])
+
+    def loop(wrapper, params, cond, train, pe, pm, **kw):
+        calls.append(("norm", [p.detach().clone() for p in params], wrapper))
+        with torch.no_grad():
+            for p in params:
+                p.add_(1.0)                      # "training" moves everything, the next video must start from the init
+        return {"losses": [0.9, 0.8], "early_stopping_info": None}
+
+    monkeypatch.setattr(cli.A, "collect_norm_params", lambda dit, target: list(norm))
+    monkeypatch.setattr(cli.A, "NormTuneForward", Wrapper)
+    monkeypatch.setattr(cli.A, "optimize_norm_params", loop)
+    s = cli.run("norm_tune", (f"--output-dir {tmp_path} --synthetic --model tiny --device cpu --latent-hw 8,8 "
+                              f"--tta-total-frames 17 --tta-context-frames 5 --max-videos 2 --es-disable --also-tune-delta").split())
+    assert [r["success"] for r in s["results"]] == [True, True]
+    for kind, seen, wrapper in calls[-2:]:
+        assert kind == "norm" and len(seen) == 3 and seen[-1].shape == (512,)
+        assert float(seen[0][0]) == 1.0 and float(seen[-1].abs().sum()) == 0.0          # reset before every video
+    cfg = json.loads((tmp_path / "config.json").read_text())
+    assert cfg["trainable_params"] == 4 + 4 + 512 and cfg["norm_tune"]["norm_target"] == "all_norm"
