@@ -9,7 +9,8 @@ forward is the one of plain norm-tune, so:
 
 Marked xfail(strict=False): this combination was written after the round's GPU budget was spent and has not run on a
 B200 yet (its host side is pinned in tests/test_adapter_loops_cpu.py); an unverified path must not be able to stop the
-suite.  Promote to a plain test once it has passed."""
+suite -- hence also the file name, which sorts it after every other GPU test.  Promote to a plain test (and rename)
+once it has passed."""
 import pytest
 import torch
 
