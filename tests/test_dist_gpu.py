@@ -50,3 +50,31 @@ def test_two_rank_nccl_replicas_stay_identical():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] == out[1]
+
+
+def test_method_script_under_torchrun(tmp_path):
+    """The LoRA script started the way a user would (torchrun, 2 ranks): both ranks finish, rank 0 writes the
+    reference's files once, early stopping ran on agreed anchor losses (tests/test_dist_cpu.py covers the host flow on
+    gloo; this is the same path on NCCL with the real engine)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(root / "lora_experiment" / "scripts" / "run_lora_tta.py"), "--output-dir", str(tmp_path),
+           "--synthetic", "--model", "tiny", "--latent-hw", "32,32", "--tta-total-frames", "17", "--tta-context-frames", "5",
+           "--lora-rank", "16", "--lora-alpha", "32", "--num-steps", "4", "--max-videos", "2", "--es-check-every", "1",
+           "--skip-generation"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    summary = json.loads((tmp_path / "summary.json").read_text())
+    assert summary["num_successful"] == 2 and summary["method"] == "lora_tta"
+    for row in summary["results"]:
+        assert row["early_stopping_info"]["total_checks"] >= 2 and row["final_loss"] > 0
+    assert json.loads((tmp_path / "checkpoint.json").read_text())["next_idx"] == 2
