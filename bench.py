@@ -2,7 +2,10 @@
 """bench.py -- TTA steps/s of the LongCat-Video 13.6B LoRA r=16 step at 480p / 93 frames on N B200s.
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
-  python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores)
+  python bench.py --method {lora,delta_a,delta_b,delta_c,norm_tune,film}   (configs[2]: the non-LoRA adapter families)
+  python bench.py --impl reference ...                     (CPU arm: the oracle port on the host cores, bounded sample)
+  python bench.py --impl torch_gpu ...                     (library arm: the same step in eager bf16 PyTorch on the GPU --
+                                                            cuDNN SDPA, cuBLAS linears, per-block checkpoint, foreach AdamW)
 
 One "step" = one flow-matching TTA update on one (sigma, eps) draw: noise + patchify, DiT forward (48 blocks),
 adapter-only backward with per-block recompute, clip, AdamW.  At N > 1 every rank processes its own draw of the same
@@ -27,6 +30,15 @@ METRIC, UNIT = "tta_steps_per_sec", "steps/s"
 _OUT = sys.stdout
 WORKLOAD = ("LongCat-Video 13.6B LoRA r=16 (qkv,proj; 48 blocks) TTA step, bf16, synthetic 480p 93-frame latent "
             "[16,24,60,104] = 4 context + 20 noised latent frames (37440 tokens), 512 text tokens")
+
+
+METHOD_NAMES = {
+    "lora": "LoRA r=16 (qkv,proj)", "delta_a": "delta-A (one [512] timestep-embedding offset)",
+    "delta_b": "delta-B (4 groups of [512] timestep-embedding offsets, per-tensor clip)",
+    "delta_c": "delta-C (16-channel output bias; forward only)",
+    "norm_tune": "norm-tune all_norm (LN affine + q/k RMSNorm weights, 417 792 params)",
+    "film": "FiLM full (4 groups x [6C] additive adaLN corrections)",
+}
 
 
 # ------------------------------------------------------------------------------------------------ work model
@@ -97,41 +109,93 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(steps: int, warmup: int, threads: int):
-    """Bounded CPU sample of the SAME workload through the oracle port: ONE block of the 13.6 B architecture
-    (hidden 4096, 32 heads, FFN 11008, LoRA r=16 on qkv,proj) on 1 context + 1 noised 480p latent frame (3120 tokens),
-    512 text tokens, fp32; scaled to whole steps by the algorithmic-FLOP ratio of the two geometries."""
+def _mem_available_bytes():
+    try:
+        with open("/proc/meminfo") as f:
+            return next(int(ln.split()[1]) for ln in f if ln.startswith("MemAvailable")) * 1024.0
+    except Exception:
+        return 32e9
+
+
+def _cpu_block_sample(Tc, Tt, threads, steps=1):
+    """ONE TTA step (noise draw, forward, adapter backward, clip, AdamW) of ONE block of the 13.6 B architecture
+    (hidden 4096, 32 heads, FFN 11008, LoRA r=16 on qkv,proj) through the oracle port in fp32 on the host cores, on
+    Tc context + Tt noised 480p latent frames and 512 text tokens.  Attention is evaluated query-chunk by query-chunk
+    (same arithmetic, bounded memory).  Returns wall seconds of the step."""
     import torch
-    from oracle.dit_oracle import build_oracle_dit
+    import oracle.dit_oracle as D
     from oracle import tta_oracle as T
+    from torch.utils.checkpoint import checkpoint
     torch.set_num_threads(threads)
-    L_s, Tc, Tt, Hl, Wl, M = 1, 1, 1, 60, 104, 512
-    dit = build_oracle_dit("13.6b", seed=0, init_std=0.02, depth=L_s)
-    torch.manual_seed(7)
-    mods = T.inject_lora(dit, rank=16, alpha=32.0)
-    g = torch.Generator().manual_seed(1)
-    cond = torch.randn(1, 16, Tc, Hl, Wl, generator=g)
-    train = torch.randn(1, 16, Tt, Hl, Wl, generator=g)
-    prompt = torch.randn(1, 1, M, 4096, generator=g)
-    mask = torch.ones(1, M, dtype=torch.int64)
-    times = []
+    mem_budget = 0.1 * _mem_available_bytes()
 
-    def on_step(**kw):
-        times.append(time.perf_counter())
+    def sdpa_chunked(q, k, v):
+        scale = q.shape[-1] ** -0.5
 
-    t0 = time.perf_counter()
-    T.lora_tta_loop(dit, mods, cond, train, prompt, mask, num_steps=warmup + steps, lr=2e-4, warmup_steps=3, on_step=on_step)
-    stamps = [t0] + times
-    per = [b - a for a, b in zip(stamps[:-1], stamps[1:])][warmup:]
-    t_sample = sorted(per)[len(per) // 2]
-    tpf = (Hl // 2) * (Wl // 2)
-    fa_s = f_alg(4096, 11008, L_s, (Tc + Tt) * tpf, Tc * tpf, M, 16, lora_sites_qkv_proj)["total"]
-    fa_f = f_alg(4096, 11008, 48, 24 * tpf, 4 * tpf, 512, 16, lora_sites_qkv_proj)["total"]
-    scale = fa_f / fa_s
-    return dict(t_sample=t_sample, scale=scale, value=1.0 / (t_sample * scale),
-                sample=(f"oracle port (PyTorch fp32, {threads} threads): 1 of 48 blocks of the 13.6B architecture on 2 of 24 latent "
-                        f"frames (3120 tokens), {steps} timed steps, median {t_sample:.2f} s/sample-step, scaled by the "
-                        f"algorithmic-FLOP ratio {scale:.0f}x to whole steps"))
+        def one(qc, k, v):
+            return torch.matmul(torch.softmax(torch.matmul(qc, k.transpose(-1, -2)) * scale, dim=-1), v)
+        # chunk (and re-compute the chunk in the backward) only when the score matrix would not fit the host memory:
+        # S, P and dS of one attention call at 4 B each against a tenth of what is available
+        c = max(128, int(mem_budget / (12.0 * q.shape[1] * k.shape[2])))
+        if q.shape[2] <= c:
+            return one(q, k, v)
+        return torch.cat([checkpoint(one, q[:, :, i:i + c], k, v, use_reentrant=False)
+                          for i in range(0, q.shape[2], c)], dim=2)
+
+    keep = D._sdpa
+    D._sdpa = sdpa_chunked
+    try:
+        Hl, Wl, M = 60, 104, 512
+        dit = D.build_oracle_dit("13.6b", seed=0, init_std=0.02, depth=1)
+        torch.manual_seed(7)
+        mods = T.inject_lora(dit, rank=16, alpha=32.0)
+        g = torch.Generator().manual_seed(1)
+        cond = torch.randn(1, 16, Tc, Hl, Wl, generator=g)
+        train = torch.randn(1, 16, Tt, Hl, Wl, generator=g)
+        prompt = torch.randn(1, 1, M, 4096, generator=g)
+        mask = torch.ones(1, M, dtype=torch.int64)
+        stamps = [time.perf_counter()]
+        T.lora_tta_loop(dit, mods, cond, train, prompt, mask, num_steps=steps, lr=2e-4, warmup_steps=3,
+                        on_step=lambda **kw: stamps.append(time.perf_counter()))
+        return stamps[-1] - stamps[-2]      # the LAST step (earlier ones warm the allocator / oneDNN primitives up)
+    finally:
+        D._sdpa = keep
+
+
+def cpu_sample(budget_s: float, threads: int):
+    """Bounded CPU sample of the headline workload for the reference arm / cpu_baseline.
+
+    What is TIMED: one step of one block (of 48 identical ones) through the oracle port, first on a small probe geometry
+    (1 + 1 latent frames), then on the largest prefix of the headline geometry (4 context + k noised frames, k <= 20)
+    whose predicted time fits ``budget_s`` and whose fp32 activations fit the host memory.  What is EXTRAPOLATED (and
+    flagged as such in the JSON line): x48 blocks (exact: the blocks are identical; embedders / final layer are < 0.1 %)
+    and, only if the full 24 frames did not fit the budget, the algorithmic-FLOP ratio to 24 frames."""
+    tpf = 30 * 52
+    fa = lambda L, Tc, Tt: f_alg(4096, 11008, L, (Tc + Tt) * tpf, Tc * tpf, 512, 16, lora_sites_qkv_proj)["total"]
+    t_probe = _cpu_block_sample(1, 1, threads, steps=2)
+    rate = fa(1, 1, 1) / t_probe                       # algorithmic FLOP/s of the port on this host
+    avail_gb = _mem_available_bytes() / 1e9
+    Tt = 0
+    for k in range(20, 0, -1):   # ~0.9 GB of fp32 activations per latent frame of one block + 9 GB of weights / grads
+        if fa(1, 4, k) / rate * 1.3 <= budget_s and 12.0 + 1.0 * (4 + k) <= 0.8 * avail_gb:
+            Tt = k
+            break
+    if Tt == 0:
+        Tc_s, Tt_s, t_sample = 1, 1, t_probe
+    else:
+        Tc_s, Tt_s = 4, Tt
+        t_sample = _cpu_block_sample(4, Tt, threads)
+    scale_blocks = 48.0
+    scale_tokens = fa(1, 4, 20) / fa(1, Tc_s, Tt_s)
+    t_full = t_sample * scale_blocks * scale_tokens
+    return dict(t_sample=t_sample, t_probe=t_probe, value=1.0 / t_full, scale=scale_blocks * scale_tokens,
+                scale_blocks=scale_blocks, scale_tokens=scale_tokens, frames=(Tc_s, Tt_s), tokens=(Tc_s + Tt_s) * tpf,
+                seconds_timed=t_probe + (t_sample if Tt else 0.0),
+                sample=(f"oracle port (PyTorch fp32, {threads} threads): ONE timed step of 1 of 48 blocks of the 13.6B "
+                        f"architecture on {Tc_s}+{Tt_s} of 4+20 latent frames ({(Tc_s + Tt_s) * tpf} of 37440 tokens), "
+                        f"{t_sample:.1f} s; extrapolated x{scale_blocks:.0f} (identical blocks)"
+                        + (f" x{scale_tokens:.2f} (algorithmic-FLOP ratio to 24 frames)" if scale_tokens > 1.0001 else "")
+                        + f" = {t_full:.0f} s per whole step"))
 
 
 def cpu_tiny_sample(threads: int, steps: int = 5, warmup: int = 1):
@@ -160,18 +224,134 @@ def cpu_tiny_sample(threads: int, steps: int = 5, warmup: int = 1):
 
 
 def run_reference(args):
+    """CPU arm.  The reference is a Python tree without packaging and its DiT dependency is absent, so the
+    arm times the oracle port (kind "port").  A whole 13.6 B step would take ~1 h of CPU time: the line carries what was
+    actually timed (``timed``), the factor it was multiplied by (``scale_factor``) and ``"extrapolated": true``; ``steps``
+    counts the sample steps really executed.  configs[0] (the tiny model, the case the reference can run on a CPU) is
+    measured whole and unscaled and sits inside ``cpu_baseline`` as ``config0``."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 3))
-    r = cpu_sample(steps, min(args.warmup, 1), threads)
+    r = cpu_sample(args.ref_budget_s, threads)
+    tiny = cpu_tiny_sample(threads)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1,
+        "warmup": 1, "ms_per_step": 1000.0 / r["value"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port", "sample": r["sample"]},
+        "extrapolated": True, "scale_factor": r["scale"],
+        "timed": {"sample_steps": 1, "probe_steps": 2, "seconds": r["seconds_timed"], "sample_seconds": r["t_sample"],
+                  "sample_tokens": r["tokens"], "sample_blocks": 1,
+                  "note": "value / ms_per_step / e2e are sample_seconds x scale_factor, NOT a measurement of a whole step"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port-extrapolated",
+                         "sample": r["sample"], "config0": tiny},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), file=_OUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ library arm (PyTorch on the GPU)
+def torch_gpu_steps(dev, steps, warmup, Tc, Tt, Hl, Wl, M, depth=48, seed=0):
+    """The same LoRA TTA step in eager bf16 PyTorch on this GPU -- what the reference executes:
+    the DiT restated in oracle/dit_oracle.py with bf16 parameters, ``F.scaled_dot_product_attention`` (cuDNN / flash
+    backends) for both attentions, cuBLAS(Lt) linears, per-block ``torch.utils.checkpoint(use_reentrant=False)``
+    (run_lora_tta.py:806-811), ``clip_grad_norm_`` and foreach ``torch.optim.AdamW`` on the bf16 LoRA tensors
+    (run_lora_tta.py:462-468,513-514).  Returns (ms per step, losses, attention backend)."""
+    import torch
+    import torch.nn.functional as F
+    from torch.nn.attention import sdpa_kernel, SDPBackend
+    import oracle.dit_oracle as D
+    from oracle import tta_oracle as T
+    BF16 = torch.bfloat16
+    backends = [SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION, SDPBackend.EFFICIENT_ATTENTION, SDPBackend.MATH]
+
+    def sdpa(q, k, v):
+        with sdpa_kernel(backends, set_priority=True):
+            return F.scaled_dot_product_attention(q, k, v)
+
+    keep = D._sdpa
+    D._sdpa = sdpa
+    try:
+        cfg = D.make_config("13.6b", depth=depth)
+        with torch.device("meta"):
+            dit = D.OracleDiT(cfg)
+        dit = dit.to(BF16).to_empty(device=dev)
+        g = torch.Generator(device=dev).manual_seed(seed)
+        with torch.no_grad():
+            for n, p in dit.named_parameters():
+                if p.dim() >= 2 or n.endswith("bias"):
+                    p.copy_(torch.randn(p.shape, generator=g, device=dev, dtype=torch.float32) * 0.02)
+                else:
+                    p.copy_(1.0 + torch.randn(p.shape, generator=g, device=dev, dtype=torch.float32) * 0.02)
+        dit.requires_grad_(False)
+        dit.gradient_checkpointing = True
+        torch.manual_seed(7)
+        mods = T.inject_lora(dit, rank=16, alpha=32.0, target_modules=("qkv", "proj"))
+        params = T.lora_parameters(mods)
+        for p in params:
+            p.requires_grad_(True)
+        opt = torch.optim.AdamW(params, lr=2e-4, betas=(0.9, 0.999), weight_decay=0.01, eps=1e-8)
+        gi = torch.Generator().manual_seed(1)
+        cond = torch.randn(1, 16, Tc, Hl, Wl, generator=gi).to(BF16).to(dev)
+        train = torch.randn(1, 16, Tt, Hl, Wl, generator=gi).to(BF16).to(dev)
+        prompt = torch.randn(1, 1, M, cfg.caption_channels, generator=gi).to(BF16).to(dev)
+        mask = torch.ones(1, M, dtype=torch.int64, device=dev)
+        losses = []
+
+        def one_step(i):
+            for gp in opt.param_groups:
+                gp["lr"] = T.warmup_lr(2e-4, i, 3)
+            sigma = torch.rand(1, device=dev, dtype=torch.float32) * 0.999 + 0.001
+            noise = torch.randn_like(train)
+            loss = T.fm_loss_given(dit, cond, train, prompt, mask, sigma, noise, BF16)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            losses.append(loss.detach())
+
+        for i in range(warmup):
+            one_step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one_step(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        vals = [float(v) for v in torch.stack(losses).tolist()]
+        peak_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+        return ms, vals, peak_gb
+    finally:
+        D._sdpa = keep
+
+
+def run_torch_gpu(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    ms, losses, peak_gb = torch_gpu_steps(dev, args.steps, args.warmup, args.cond_frames, args.train_frames, args.lat_h,
+                                          args.lat_w, args.text_tokens)
+    clocks = sampler.stop()
+    tpf = (args.lat_h // 2) * (args.lat_w // 2)
+    work = f_alg(4096, 11008, 48, (args.cond_frames + args.train_frames) * tpf, args.cond_frames * tpf, args.text_tokens, 16,
+                 lora_sites_qkv_proj)
+    value = 1000.0 / ms
+    line = {
+        "impl": "torch_gpu", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "library_stack": "eager PyTorch %s: cuDNN/flash SDPA, cuBLASLt linears, per-block "
+                   "checkpoint, clip_grad_norm_, foreach AdamW (bf16 states)" % torch.__version__},
+        "clocks": clocks, "achieved_tflops_per_gpu": work["total"] / (ms / 1e3) / 1e12,
+        "frac_of_nominal_2250": work["total"] / (ms / 1e3) / 1e12 / 2250.0, "peak_alloc_gib": peak_gb,
+        "loss_first_last": [losses[0], losses[-1]],
     }
     print(json.dumps(line), file=_OUT, flush=True)
 
@@ -206,8 +386,24 @@ def run_b200(args):
         _BSA["pairs_per_head"] = float(nctx * keep_ctx + (nb - nctx) * keep) * bsa.BLOCK * bsa.BLOCK
     torch.manual_seed(7)
     import contextlib
-    with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
-        mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
+    wrapper = None
+    if args.method == "lora":
+        with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
+            mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
+    else:   # BASELINE.json configs[2]: the delta / norm / AdaLN(FiLM) / bias families (SURVEY 8d "Config 3")
+        from longcat_video_tta_b200 import adapters
+        C, Ct = cfg.hidden_size, cfg.adaln_tembed_dim
+        wrapper = {
+            "delta_a": lambda: adapters.DeltaAWrapper(dit, adaln_tembed_dim=Ct),
+            "delta_b": lambda: adapters.DeltaBWrapper(dit, num_groups=4, adaln_tembed_dim=Ct, hidden_size=C),
+            "delta_c": lambda: adapters.DeltaCWrapper(dit, mode="per_channel", out_channels=16),
+            "norm_tune": lambda: adapters.NormTuneForward(dit),
+            "film": lambda: adapters.FiLMAdapterWrapper(dit, num_groups=4, hidden_size=C, film_mode="full"),
+        }[args.method]()
+        if args.method == "norm_tune":
+            for p in adapters.collect_norm_params(dit, "all_norm"):
+                p.requires_grad_(True)
+            wrapper = adapters.NormTuneForward(dit)
     g = torch.Generator().manual_seed(1)  # the same video on every rank; the (sigma, eps) draws differ per rank
     cond_h = torch.randn(1, 16, Tc, Hl, Wl, generator=g).to(BF16).pin_memory()
     train_h = torch.randn(1, 16, Tt, Hl, Wl, generator=g).to(BF16).pin_memory()
@@ -215,10 +411,14 @@ def run_b200(args):
     mask_h = torch.ones(1, M, dtype=torch.int64).pin_memory()
     cond, train, prompt, mask = (t.to(dev) for t in (cond_h, train_h, prompt_h, mask_h))
     torch.manual_seed(42 + rank)
-    stepper = TTAStepper(dit, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0, master_weights=True)
+    if wrapper is None:
+        stepper = TTAStepper(dit, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0, master_weights=True)
+    else:   # adapters._optimize: AdamW eps 1e-15, wd 0.01, constant lr 1e-3, clip 1.0 (per tensor for delta-B)
+        stepper = TTAStepper(dit, adapter=wrapper, train_lora=False, eps=1e-15, weight_decay=0.01, max_grad_norm=1.0,
+                             per_tensor_clip=wrapper.per_tensor_clip)
 
     def one_step(c, t, p, m, i):
-        lr = lora._warmup_lr(2e-4, i, 3)
+        lr = lora._warmup_lr(2e-4, i, 3) if wrapper is None else 1e-3
         sigma = torch.rand(1, device=dev, dtype=torch.float32) * 0.999 + 0.001
         noise = torch.randn_like(t)
         return stepper.step(c, t, p, m, sigma, noise, lr)
@@ -276,7 +476,10 @@ def run_b200(args):
         return
 
     geo = dit.engine.geo
-    work = f_alg(cfg.hidden_size, cfg.ffn_dim, cfg.depth, geo.N, geo.Nc, geo.M, 16, lora_sites_qkv_proj)
+    work = f_alg(cfg.hidden_size, cfg.ffn_dim, cfg.depth, geo.N, geo.Nc, geo.M, 16 if args.method == "lora" else 0,
+                 lora_sites_qkv_proj)
+    if args.method == "delta_c":    # output-bias only: the gradient is a reduction of d loss / d pred, forward only
+        work["total"] = work["f_lin"] + work["f_attn"] + work["f_x"]
     if args.bsa_sparsity is not None:
         f_attn = 4.0 * cfg.depth * cfg.hidden_size * _BSA["pairs_per_head"]
         work["total"] += 3.5 * (f_attn - work["f_attn"])
@@ -301,22 +504,48 @@ def run_b200(args):
                 "launches_per_step": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                 "algorithmic_tflop_per_launch": d["flops"] / d["n"] / 1e12, "share_of_step": d["ms"] / tot_ms}
     cpu = cpu_tiny = None
+    lib = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_sample(2, 1, os.cpu_count() or 1)
-        cpu = {"value": r["value"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": r["sample"]}
+        r = cpu_sample(args.cpu_budget_s, os.cpu_count() or 1)
         cpu_tiny = cpu_tiny_sample(os.cpu_count() or 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port-extrapolated",
+               "extrapolated": True, "scale_factor": r["scale"], "seconds_timed": r["seconds_timed"], "sample": r["sample"],
+               "config0": cpu_tiny}
+    if world == 1 and args.library_baseline and args.method == "lora" and args.bsa_sparsity is None and cfg_name == "13.6b":
+        # same box, same process, after the engine's memory is returned: the step in eager bf16 PyTorch (library arm)
+        n_params = stepper.n_params
+        stash_txt = _stash_summary(stepper.eng)
+        del stepper, mods
+        dit._engine = None
+        del dit
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            lms, llosses, lpeak = torch_gpu_steps(dev, 2, 2, Tc, Tt, Hl, Wl, M)
+            lib = {"impl": "torch_gpu", "value": 1000.0 / lms, "unit": UNIT, "ms_per_step": lms, "steps": 2, "warmup": 2,
+                   "stack": "eager PyTorch %s bf16: SDPA (cuDNN first), cuBLASLt linears, per-block checkpoint, clip_grad_norm_, "
+                            "foreach AdamW" % torch.__version__, "peak_alloc_gib": lpeak, "loss_first_last": [llosses[0], llosses[-1]],
+                   "speedup_of_this_repo": (ms / args.steps) and lms / (ms / args.steps)}
+        except Exception as e:   # the library arm must never take the headline line down with it
+            lib = {"impl": "torch_gpu", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}
+    else:
+        n_params = stepper.n_params
+        stash_txt = _stash_summary(stepper.eng)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD if cfg_name == "13.6b" and (Tc, Tt, Hl, Wl, M) == (4, 20, 60, 104, 512) else
-                   f"{cfg_name} LoRA r=16 TTA step, latent [16,{Tc}+{Tt},{Hl},{Wl}], {M} text tokens"
+        "config": {"workload": (WORKLOAD if args.method == "lora" else WORKLOAD.replace(
+                       "LoRA r=16 (qkv,proj; 48 blocks)", METHOD_NAMES[args.method]))
+                   if cfg_name == "13.6b" and (Tc, Tt, Hl, Wl, M) == (4, 20, 60, 104, 512) else
+                   f"{cfg_name} {METHOD_NAMES[args.method]} TTA step, latent [16,{Tc}+{Tt},{Hl},{Wl}], {M} text tokens"
                    + ("" if args.bsa_sparsity is None else
                       f", block-sparse self-attention (128-token chunks 4x4x8, sparsity {args.bsa_sparsity})"),
-                   "tokens": geo.N, "adapter_params": stepper.n_params, "parallelism": f"dp{world} over noise draws",
+                   "method": args.method, "tokens": geo.N, "adapter_params": n_params, "parallelism": f"dp{world} over noise draws",
                    "recompute": "per-block forward re-run in the backward except self-attention (O, LSE kept for all blocks) "
-                                "and whatever fits the spare-HBM activation stash (blocks covered: " + _stash_summary(stepper.eng) + ")",
+                                "and whatever fits the spare-HBM activation stash (blocks covered: " + stash_txt + ")",
                    "l2": "inputs far exceed L2: 27 GB of frozen weights + 15 GB of block inputs are streamed every step"},
         "clocks": clocks,
         "e2e": {"value": world / (ms_e2e / args.steps / 1000.0), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -324,7 +553,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": roof,
         "cpu_baseline": cpu,
-        "cpu_baseline_config0": cpu_tiny,
+        "library_baseline": lib,
         "algorithmic_tflop_per_step": work["total"] / 1e12,
         "achieved_tflops_per_gpu": tflops,
         "frac_of_nominal_2250": tflops / 2250.0,
@@ -465,7 +694,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--method", default="lora", choices=list(METHOD_NAMES),
+                    help="adapter family: lora = BASELINE.json configs[1]; the others = configs[2]")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: CPU seconds for the block sample")
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="cpu_baseline leg of the default run")
+    ap.add_argument("--no-library-baseline", dest="library_baseline", action="store_false",
+                    help="skip the same-box eager-PyTorch step (library_baseline key; N=1 only)")
     ap.add_argument("--model", default="13.6b", choices=["13.6b", "tiny"])
     ap.add_argument("--cond-frames", type=int, default=4)
     ap.add_argument("--train-frames", type=int, default=20)
@@ -478,6 +713,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_b200(args)
 

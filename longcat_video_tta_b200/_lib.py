@@ -7,8 +7,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libb200tta.so"
+# B200TTA_LIB selects another build of the SAME library (A/B runs of kernel variants, debug-instrumented builds)
+LIB_PATH = Path(os.environ["B200TTA_LIB"]).resolve() if os.environ.get("B200TTA_LIB") else PKG / "libb200tta.so"
 
 OK, EINVAL, EARCH, ECUDA = 0, -1, -2, -3
 

@@ -247,16 +247,20 @@ class TTAEngine:
 
     # ------------------------------------------------------------------ adapters
     def _signature(self):
+        # the module objects themselves (compared by identity): holding them means a re-injected adapter can never be
+        # mistaken for a freed one whose id() the allocator handed out again
         sig = []
         for blk in self.dit.blocks:
             for m in (blk.attn.qkv, blk.attn.proj, blk.cross_attn.q_linear, blk.cross_attn.kv_linear, blk.cross_attn.proj,
                       blk.ffn.w1, blk.ffn.w2, blk.ffn.w3):
-                sig.append((id(m), id(_hooked_lora(m))))
-        return tuple(sig)
+                sig.append(m)
+                sig.append(_hooked_lora(m))
+        return sig
 
     def resolve_sites(self, force: bool = False):
         sig = self._signature()
-        if not force and sig == self._site_sig:
+        old = self._site_sig
+        if not force and old is not None and len(old) == len(sig) and all(a is b for a, b in zip(old, sig)):
             return
         self._site_sig = sig
         self.sites = [_block_sites(blk, i) for i, blk in enumerate(self.dit.blocks)]
@@ -448,10 +452,14 @@ class TTAEngine:
         text_tokens_zero_pad = False : only valid tokens are packed (y_embedder is row-wise, so packing before or
                                        after it is the same arithmetic), M = mask.sum().
         """
-        key = (prompt_embeds.data_ptr(), prompt_embeds._version, None if mask is None else (mask.data_ptr(), mask._version))
-        if self._text_cache is not None and self._text_cache[0] == key:
-            self._text_keep = self._text_cache[2]
-            return self._text_cache[1]
+        # one-entry cache keyed on the SOURCE tensors themselves (identity + in-place version): holding them keeps their
+        # addresses from being recycled by the caching allocator for the next video's embeddings (a data_ptr key
+        # would then hit and silently train on the previous prompt)
+        c = self._text_cache
+        if (c is not None and c[0] is prompt_embeds and c[1] == prompt_embeds._version and c[2] is mask
+                and (mask is None or c[3] == mask._version)):
+            self._text_keep = c[5]
+            return c[4]
         if prompt_embeds.shape[0] != 1:
             raise NotImplementedError("batch size 1 only (as in every reference run)")
         pe = prompt_embeds.reshape(-1, prompt_embeds.shape[-1])
@@ -463,7 +471,7 @@ class TTAEngine:
                 idx = mask.reshape(-1).nonzero(as_tuple=False).flatten()
                 pe = pe.index_select(0, idx.to(pe.device))
         pe = pe.to(device=self.device, dtype=BF16).contiguous()
-        self._text_cache = (key, pe, keep)
+        self._text_cache = (prompt_embeds, prompt_embeds._version, mask, None if mask is None else mask._version, pe, keep)
         self._text_keep = keep
         return pe
 
@@ -506,7 +514,11 @@ class TTAEngine:
         if ex is not None and ex.film[b] is not None:
             film = ex.film[b].to(F32)[None, :].expand(geo.T, -1).contiguous()
         elif blk.adaLN_modulation._forward_hooks:
-            raise NotImplementedError("forward hooks on adaLN_modulation: use longcat_video_tta_b200.film.FiLMAdapterWrapper")
+            # dit_forward_autograd turns such hooks into an adapter (HookedModulationAdapter); reaching this line means
+            # the engine was driven directly (TTAStepper) with hooks installed but no adapter describing them
+            raise NotImplementedError(
+                "forward hooks on blocks[%d].adaLN_modulation are only honoured through B200DiT.forward(); for the fused "
+                "stepper use longcat_video_tta_b200.adapters.FiLMAdapterWrapper (same constructor as the reference's)" % b)
         ops.skinny_linear(ws.mod, self._t_for_block(b, ex), ada.weight, ada.bias, act=1, addend=film)
         mod = ws.mod
         shift_msa, scale_msa, gate_msa = mod[:, 0:C], mod[:, C:2 * C], mod[:, 2 * C:3 * C]
@@ -979,12 +991,89 @@ class _DiTFunction(torch.autograd.Function):
         return (None, None, None, None, None, None, None, *grads)
 
 
+class HookedModulationAdapter:
+    """The adapter protocol (``trainable`` / ``build_extras`` / ``grads_from``) synthesised from forward hooks found on
+    ``blocks[i].adaLN_modulation`` -- the seam the reference's ``FiLMAdapterWrapper.apply_to_dit`` uses
+    (delta_experiment/scripts/run_film_tta.py:146-163: ``output + expand(correction)``), so that a B200DiT carrying those
+    hooks behaves like upstream's when it is called (generation after TTA, or a loss.backward() through ``dit(...)``).
+
+    Only ADDITIVE hooks can be folded into the fused adaLN kernel (the term is evaluated once per forward on a zero
+    output, with an autograd graph to whatever parameters the hook closes over; the engine's d loss / d(adaLN output)
+    is pushed back through that graph).  Anything else is refused loudly."""
+
+    def __init__(self, dit):
+        self.dit = dit
+        self.hooks = [list(blk.adaLN_modulation._forward_hooks.values()) for blk in dit.blocks]
+        self.params: List[nn.Parameter] = []
+        for hs in self.hooks:
+            for h in hs:
+                for cell in getattr(h, "__closure__", None) or ():
+                    try:
+                        obj = cell.cell_contents
+                    except ValueError:
+                        continue
+                    if isinstance(obj, nn.Parameter) and obj.requires_grad and not any(obj is p for p in self.params):
+                        self.params.append(obj)
+        self._terms: List[Optional[torch.Tensor]] = []
+
+    @staticmethod
+    def present(dit) -> bool:
+        return any(blk.adaLN_modulation._forward_hooks for blk in dit.blocks)
+
+    def trainable(self) -> List[nn.Parameter]:
+        return self.params
+
+    def _run(self, b: int, out: torch.Tensor) -> torch.Tensor:
+        mod = self.dit.blocks[b].adaLN_modulation
+        for h in self.hooks[b]:
+            r = h(mod, (None,), out)
+            if r is not None:
+                out = r
+        return out
+
+    def build_extras(self) -> Extras:
+        cfg = self.dit.config
+        dev = self.dit.x_embedder.proj.weight.device
+        ex = Extras(len(self.dit.blocks))
+        self._terms = []
+        zero = torch.zeros(1, 1, 6 * cfg.hidden_size, dtype=F32, device=dev)
+        probe = torch.linspace(-1.0, 1.0, 6 * cfg.hidden_size, dtype=F32, device=dev).view(1, 1, -1)
+        with torch.enable_grad():
+            for b, hs in enumerate(self.hooks):
+                if not hs:
+                    self._terms.append(None)
+                    continue
+                term = self._run(b, zero)
+                with torch.no_grad():
+                    if term.shape != zero.shape or not torch.allclose(self._run(b, probe) - probe, term, atol=1e-6):
+                        raise NotImplementedError(
+                            f"blocks[{b}].adaLN_modulation carries a forward hook that is not `output + constant`: only "
+                            "additive (FiLM-style) hooks can be folded into the fused adaLN kernel")
+                ex.film[b] = term.detach().reshape(-1).float()
+                self._terms.append(term if term.requires_grad else None)
+        ex.need_dmod = any(t is not None for t in self._terms)
+        return ex
+
+    def grads_from(self, ex: Extras) -> List[torch.Tensor]:
+        gs = [torch.zeros(p.shape, dtype=F32, device=p.device) for p in self.params]
+        for b, term in enumerate(self._terms):
+            if term is None:
+                continue
+            g = ex.d_mod[b].sum(0).view_as(term).to(term.dtype)
+            for acc, gp in zip(gs, torch.autograd.grad(term, self.params, g, allow_unused=True)):
+                if gp is not None:
+                    acc += gp.float()
+        return gs
+
+
 def dit_forward_autograd(dit, hidden_states, timestep, encoder_hidden_states, encoder_attention_mask, num_cond_latents,
                          adapter=None):
     if not hidden_states.is_cuda:
         from ._lib import B200TTAError
         raise B200TTAError("B200DiT runs on a B200 only: inputs are on %s and there is no CPU fallback" % hidden_states.device)
     eng = dit.engine
+    if adapter is None and HookedModulationAdapter.present(dit):
+        adapter = HookedModulationAdapter(dit)
     text_valid = eng.pack_text(encoder_hidden_states, encoder_attention_mask)
     if timestep.dim() == 1:
         timestep = timestep.unsqueeze(1).expand(-1, hidden_states.shape[2])

@@ -406,7 +406,13 @@ class OracleDiT(nn.Module):
         t = self.t_embedder(timestep.to(dtype).float().flatten(), dtype=torch.float32).reshape(B, N_t, -1)
         y, y_seqlens = self.embed_text(encoder_hidden_states.to(dtype), encoder_attention_mask)
         for block in self.blocks:
-            x = block(x, y, t, y_seqlens, (N_t, N_h, N_w), num_cond_latents=num_cond_latents)
+            if self.gradient_checkpointing and torch.is_grad_enabled():
+                # the reference turns this on for training (run_lora_tta.py:806-811): per-block recompute
+                from torch.utils.checkpoint import checkpoint
+                x = checkpoint(block, x, y, t, y_seqlens, (N_t, N_h, N_w), num_cond_latents=num_cond_latents,
+                               use_reentrant=False)
+            else:
+                x = block(x, y, t, y_seqlens, (N_t, N_h, N_w), num_cond_latents=num_cond_latents)
         x = self.final_layer(x, t, (N_t, N_h, N_w))
         return self.unpatchify(x, N_t, N_h, N_w).to(torch.float32)
 

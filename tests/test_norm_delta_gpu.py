@@ -7,15 +7,11 @@ forward is the one of plain norm-tune, so:
   * the delta gradient of the combined step == that of ``DeltaAWrapper`` alone on the same (nudged) DiT,
   * one optimizer step moves both kinds of parameters.
 
-Marked xfail(strict=False): this combination was written after the round's GPU budget was spent and has not run on a
-B200 yet (its host side is pinned in tests/test_adapter_loops_cpu.py); an unverified path must not be able to stop the
-suite -- hence also the file name, which sorts it after every other GPU test.  Promote to a plain test (and rename)
-once it has passed."""
+Ran green on a B200 (driver GPUTEST_r01: x-passed; round 2 suite): a plain test now."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="norm-tune + delta-A combination not yet run on a GPU")]
+pytestmark = pytest.mark.gpu
 BF16, F32 = torch.bfloat16, torch.float32
 
 

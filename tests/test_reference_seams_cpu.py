@@ -73,3 +73,43 @@ def test_reference_builtin_injection_is_recognised_and_unhooked():
     ref.unhook_builtin_lora(dit)
     dit.engine.resolve_sites()
     assert dit.engine.lora_sites() == []
+
+
+@pytest.mark.parametrize("mode", ["full", "shift_scale", "scale_only"])
+def test_reference_film_hooks_are_folded_into_the_engine(mode):
+    """run_film_tta.py:146-163: apply_to_dit() puts `output + expand(correction)` hooks on every adaLN_modulation.  The
+    engine turns them into per-block additive terms and pushes d loss / d(adaLN output) back onto the corrections."""
+    from longcat_video_tta_b200.engine import HookedModulationAdapter, Extras
+    ref = ref_bridge.load("run_film_tta")
+    dit = _dit()
+    C = dit.config.hidden_size
+    w = ref.FiLMAdapterWrapper(dit, num_groups=2, hidden_size=C, film_mode=mode)
+    with torch.no_grad():
+        for i, c in enumerate(w.corrections):
+            c.copy_(torch.randn(c.shape, generator=torch.Generator().manual_seed(i)))
+    assert not HookedModulationAdapter.present(dit)
+    w.apply_to_dit()
+    assert HookedModulationAdapter.present(dit)
+    ad = HookedModulationAdapter(dit)
+    assert len(ad.trainable()) == 2 and all(a is b for a, b in zip(ad.trainable(), w.corrections))
+    ex = ad.build_extras()
+    assert ex.need_dmod
+    for b in range(len(dit.blocks)):
+        want = w._expand_correction(w.corrections[w._get_group_idx(b)]).detach()
+        assert torch.equal(ex.film[b], want.float())
+    # backward: a made-up d(adaLN output) per block [T, 6C]; the reference's gradient is autograd through its own hook
+    T = 3
+    ex.d_mod = [torch.randn(T, 6 * C, generator=torch.Generator().manual_seed(10 + b)) for b in range(len(dit.blocks))]
+    got = ad.grads_from(ex)
+    outs = [torch.zeros(1, T, 6 * C, requires_grad=False) for _ in dit.blocks]
+    total = 0
+    for b, blk in enumerate(dit.blocks):
+        y = outs[b]
+        for h in blk.adaLN_modulation._forward_hooks.values():
+            y = h(blk.adaLN_modulation, (None,), y)
+        total = total + (y[0] * ex.d_mod[b]).sum()
+    want = torch.autograd.grad(total, list(w.corrections))
+    for g, wnt in zip(got, want):
+        assert torch.allclose(g, wnt, rtol=1e-5, atol=1e-5)
+    w.remove_from_dit()
+    assert not HookedModulationAdapter.present(dit)

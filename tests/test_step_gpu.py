@@ -104,14 +104,17 @@ def bf16_torch_grads(oracle, adapter_seed, cond, train, prompt, mask, sigma, eps
 def test_autograd_path_grads_match_golden_and_oracle(setup, golden_dir):
     """dit(...) + the reference-style loss + loss.backward(): the drop-in seam (common.py:476-488).
 
-    Three-way comparison of the step-0 adapter gradients:
-      golden  fp32 CPU, produced by the reference's own code           (tests/golden/lora_tiny.pt)
+    Four-way comparison of the step-0 adapter gradients:
+      fp32    the oracle in fp32 arithmetic on the bf16-VALUED weights / inputs the GPU path stores   <- north-star bar
+      golden  fp32 CPU with UN-ROUNDED fp32 weights, produced by the reference's own code (tests/golden/lora_tiny.pt)
       bf16    the identical step in plain bf16 PyTorch on this GPU      (the arithmetic the reference really runs)
       mine    the sm_100a kernels
-    On this tiny random-init model bf16 storage alone costs ~5 % of gradient direction on the self-attention adapters
-    (near-uniform attention makes dS = P o (dP - delta) a small difference of large numbers), so the fp32 bound that
-    can be asserted is "at least as close to fp32 as bf16 PyTorch is"; against bf16 PyTorch itself the north-star
-    tolerance (cosine > 0.999, norm within 2e-2) holds for every tensor.
+    North-star tolerance (cosine > 0.999, norm within 2e-2) is asserted against ``fp32`` and against ``bf16`` for every
+    tensor.  The golden run differs from all three others by the storage format of the frozen backbone (its weights
+    were never rounded to bf16; the reference's GPU backbone is bf16): on this tiny random-init model that alone moves
+    the self-attention adapter gradients to cosine ~0.98, for bf16 PyTorch exactly as for the kernels (round 1 mistook
+    this for kernel error; tests/test_block_parity_gpu.py separates the two).  Against the golden the bound is therefore
+    "at least as close as bf16 PyTorch is".
     """
     from oracle import tta_oracle as T
     from longcat_video_tta_b200 import lora
@@ -131,6 +134,24 @@ def test_autograd_path_grads_match_golden_and_oracle(setup, golden_dir):
     loss = T.fm_loss_given(dit, cond, train, prompt, mask, sigma, eps, BF16)
     loss.backward()
     bloss, bgrads = bf16_torch_grads(s["oracle"], g["config"]["adapter_seed"], cond, train, prompt, mask, sigma, eps)
+    # fp32 arithmetic on the same bf16-valued weights and adapter factors (TF32 off)
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        ro = rounded_oracle(s["oracle"])
+        torch.manual_seed(g["config"]["adapter_seed"])
+        romods = T.inject_lora(ro, rank=16, alpha=32.0, target_modules=("qkv", "proj"))
+        with torch.no_grad():
+            for m, om in zip(mods, romods):
+                om.lora_down.weight.copy_(m.lora_down.weight.float())
+        rparams = T.lora_parameters(romods)
+        for p in rparams:
+            p.requires_grad_(True)
+        rloss = T.fm_loss_given(ro, cond, train, prompt, mask, sigma, eps, BF16)
+        rgrads = torch.autograd.grad(rloss, rparams)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    assert abs(loss.item() - rloss.item()) <= 2e-2 * rloss.item()
     print(f"loss mine {loss.item():.6f} bf16-torch {bloss:.6f} golden(fp32 reference) {g['losses'][0]:.6f}")
     assert abs(loss.item() - g["losses"][0]) <= 2e-2 * g["losses"][0]
     # golden holds CLIPPED grads of step 0; clipping is a positive scalar -> compare directions + norm ratio
@@ -138,13 +159,16 @@ def test_autograd_path_grads_match_golden_and_oracle(setup, golden_dir):
     total = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in params)).item()
     coef = min(1.0, 1.0 / (total + 1e-6))
     mine_all, gold_all = [], []
-    for i, (p, want, bg) in enumerate(zip(params, gold, bgrads)):
+    for i, (p, want, bg, rg) in enumerate(zip(params, gold, bgrads, rgrads)):
         got = p.grad.float().cpu() * coef
         if i % 2 == 0:   # KAT: B == 0 at init => dA == 0 exactly
             assert got.abs().max() == 0 and want.abs().max() == 0
             continue
-        c_gold, c_bf, c_bf_gold = cos(got, want), cos(p.grad, bg), cos(bg.cpu(), want)
-        print(f"param {i:2d}: mine~golden {c_gold:.5f}  bf16-torch~golden {c_bf_gold:.5f}  mine~bf16-torch {c_bf:.6f}")
+        c_gold, c_bf, c_bf_gold, c_fp32 = cos(got, want), cos(p.grad, bg), cos(bg.cpu(), want), cos(p.grad, rg)
+        print(f"param {i:2d}: mine~fp32(same weights) {c_fp32:.6f}  mine~bf16-torch {c_bf:.6f}  "
+              f"mine~golden {c_gold:.5f}  bf16-torch~golden {c_bf_gold:.5f}")
+        assert c_fp32 > 0.999, f"param {i}: cosine vs the fp32 oracle on the same weights {c_fp32}"
+        assert abs(p.grad.float().norm() / rg.float().norm() - 1) < 2e-2
         assert c_bf > 0.999, f"param {i}: cosine vs bf16 PyTorch {c_bf}"
         assert abs(p.grad.float().norm() / bg.float().norm() - 1) < 2e-2
         assert c_gold >= min(0.999, c_bf_gold - 5e-3), f"param {i}: {c_gold} vs bf16 PyTorch's {c_bf_gold}"
