@@ -146,6 +146,19 @@ int b200tta_attn_bwd(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, i
                      int32_t heads, float softmax_scale, const b200tta_attn_seg* segs, int32_t n_seg,
                      b200tta_stream_t stream);
 
+/* Same contract as b200tta_attn_bwd, computed by ONE kernel per (key block, head) that forms exactly the five necessary
+ * products per (query tile, key block) pair (S^T, dP^T, dV, dK and the dQ partial product) instead of the seven of the
+ * dq + dkv pair.  dQ partial tiles leave through fp32 reduce-adds into `dq_acc` -- caller-provided workspace,
+ * [heads, n_q, 128] f32 (n_q * heads * 128 floats), contents irrelevant on entry (zeroed here) -- and are converted to bf16 `dQ` at the end.
+ * The summation order of the partial tiles is not fixed run to run (differences at fp32 rounding level).
+ * Replaces the same reference call as b200tta_attn_bwd: loss.backward() through flash-attn's backward
+ * (lora_experiment/scripts/run_lora_tta.py:512). */
+int b200tta_attn_bwd_fused(void* dQ, int64_t lddq, void* dK, int64_t lddk, void* dV, int64_t lddv, const void* dO,
+                           int64_t lddo, const void* O, int64_t ldo, const float* LSE, float* delta, const void* Q,
+                           int64_t ldq, const void* K, int64_t ldk, const void* V, int64_t ldv, int32_t n_q, int32_t n_kv,
+                           int32_t heads, float softmax_scale, const b200tta_attn_seg* segs, int32_t n_seg,
+                           float* dq_acc, b200tta_stream_t stream);
+
 /* Block-sparse self-attention for the 720p refinement stage (upstream `enable_bsa` / `bsa_params`, flags at
  * delta_experiment/scripts/common.py:71-74; the upstream kernel is not vendored -- SURVEY App. A.9 -- so the block
  * semantics below are OUR definition).  Tokens are in BLOCK-MAJOR order (the 128 tokens of one 3-D chunk are

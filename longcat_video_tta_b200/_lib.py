@@ -52,6 +52,8 @@ SIGNATURES = {
     "b200tta_attn_fwd": [vp, i64, vp, vp, i64, vp, i64, vp, i64, i32, i32, i32, f32, C.POINTER(AttnSeg), i32, vp],
     "b200tta_attn_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32,
                          i32, f32, C.POINTER(AttnSeg), i32, vp],
+    "b200tta_attn_bwd_fused": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32,
+                               i32, f32, C.POINTER(AttnSeg), i32, vp, vp],
     "b200tta_attn_bsa_fwd": [vp, i64, vp, vp, i64, vp, i64, vp, i64, i32, i32, f32, vp, vp, vp],
     "b200tta_attn_bsa_bwd": [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, i64, vp, i64, vp, i64, i32, i32, f32,
                              vp, vp, vp, vp, vp],

@@ -8,7 +8,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#include "../../include/b200tta.h"
+#include "b200tta.h"
 
 namespace b200 {
 

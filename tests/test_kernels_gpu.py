@@ -389,13 +389,22 @@ def test_attn_fwd_cross_attention_shape(ops):
     close(lse, rl, rtol=1e-3, atol=1e-2)
 
 
+@pytest.fixture(params=["fused", "split"])
+def bwd_mode(request, monkeypatch):
+    """both backward implementations behind b200tta_attn_bwd*: the fused five-product kernel (default) and the
+    dq + dkv pair (B200TTA_ATTN_BWD=split; also what the block-sparse path runs)"""
+    monkeypatch.setenv("B200TTA_ATTN_BWD", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("n,H,segs", [
     (256, 2, [(0, 256, 256)]),
     (1024, 4, [(0, 512, 512), (512, 1024, 1024)]),
     (1000, 3, [(0, 390, 390), (390, 1000, 1000)]),
     (3120, 2, [(0, 1560, 1560), (1560, 3120, 3120)]),
+    (1337, 2, [(0, 200, 200), (200, 1337, 1337)]),           # no boundary on a tile edge
 ])
-def test_attn_bwd(ops, n, H, segs):
+def test_attn_bwd(ops, bwd_mode, n, H, segs):
     D = 128
     scale = D ** -0.5
     qkv = rnd(n, 3, H, D, seed=1)
@@ -416,7 +425,7 @@ def test_attn_bwd(ops, n, H, segs):
     close(dqkv[:, 2], vf.grad)
 
 
-def test_attn_bwd_cross_attention_shape(ops):
+def test_attn_bwd_cross_attention_shape(ops, bwd_mode):
     n, M, H, D = 700, 128, 4, 128
     scale = D ** -0.5
     q, kv = rnd(n, H, D, seed=1), rnd(M, 2, H, D, seed=2)
@@ -474,7 +483,7 @@ def test_attn_fwd_headline_size_properties_and_slices(ops, headline_attention):
                 close(lse[h, rows], torch.logsumexp(s, -1), rtol=1e-3, atol=1e-2)
 
 
-def test_attn_bwd_headline_size_properties_and_slices(ops, headline_attention):
+def test_attn_bwd_headline_size_properties_and_slices(ops, bwd_mode, headline_attention):
     q, k, v, o, lse = headline_attention
     scale = HEAD_D ** -0.5
     do = rnd(HEAD_N, HEAD_H, HEAD_D, seed=12)
