@@ -310,6 +310,7 @@ def torch_gpu_steps(dev, steps, warmup, Tc, Tt, Hl, Wl, M, depth=48, seed=0):
             opt.zero_grad(set_to_none=True)
             losses.append(loss.detach())
 
+        torch.cuda.reset_peak_memory_stats(dev)
         for i in range(warmup):
             one_step(i)
         torch.cuda.synchronize()

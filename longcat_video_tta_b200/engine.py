@@ -221,6 +221,24 @@ class _WS:
     pass
 
 
+class _Range:
+    """NVTX range around a phase (B200TTA_NVTX=1): forward / backward of every block show up by name in nsys / ncu
+    timelines; a no-op otherwise."""
+    on = bool(os.environ.get("B200TTA_NVTX"))
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if _Range.on:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Range.on:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 # ---------------------------------------------------------------------------------------------------- engine
 class TTAEngine:
     def __init__(self, dit):
@@ -871,10 +889,11 @@ class TTAEngine:
         self._embed_time()
         self._embed_text(text_valid)
         for b in range(self.L):
-            if ctx == "use":
-                self._block_fwd_noise_rows(b, ws.xs[b], ws.xs[b + 1], ex)
-            else:
-                self._block_fwd(b, ws.xs[b], ws.xs[b + 1], ex)
+            with _Range(f"fwd.block{b}"):
+                if ctx == "use":
+                    self._block_fwd_noise_rows(b, ws.xs[b], ws.xs[b + 1], ex)
+                else:
+                    self._block_fwd(b, ws.xs[b], ws.xs[b + 1], ex)
         if ctx is not None:
             self._ctx["valid"] = True
             self._ctx_fill = False
@@ -922,8 +941,10 @@ class TTAEngine:
             ex.d_hidden_final = ws.dx.float().sum(0)
         for b in reversed(range(self.L)):
             if getattr(self, "_ws_holds", None) != b:  # the last block's intermediates are still in the workspace
-                self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
-            self._block_bwd(b, ws.xs[b], ex)
+                with _Range(f"recompute.block{b}"):
+                    self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
+            with _Range(f"bwd.block{b}"):
+                self._block_bwd(b, ws.xs[b], ex)
         self._ws_holds = None
         self._stash_on = False
 

@@ -10,6 +10,7 @@ all-reduced once per step with NCCL; the 1/world scale is folded into the clip /
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -37,7 +38,7 @@ class TTAStepper:
     def __init__(self, dit, *, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, per_tensor_clip: bool = False, master_weights: bool = True,
                  faithful_bf16: bool = False, adapter=None, train_lora: bool = True, build_optimizer: bool = True,
-                 process_group=None):
+                 process_group=None, cuda_graph: Optional[bool] = None):
         """
         master_weights : keep an fp32 master copy (and fp32 Adam moments) of every bf16 adapter tensor.  The
                          reference keeps params and moments in bf16 (run_lora_tta.py:332) where updates below half an
@@ -49,6 +50,7 @@ class TTAStepper:
         """
         self.dit = dit
         self.eng: TTAEngine = dit.engine
+        self.cuda_graph = bool(os.environ.get("B200TTA_CUDA_GRAPH")) if cuda_graph is None else bool(cuda_graph)
         self.betas, self.eps, self.wd, self.max_norm = betas, eps, weight_decay, max_grad_norm
         self.faithful = faithful_bf16
         self.adapter = adapter
@@ -101,8 +103,47 @@ class TTAStepper:
             raise NotImplementedError("batch size 1 only (every reference run; common.py:448)")
         return Geometry(T=Tc + target.shape[2], Hl=Hl, Wl=Wl, n_cond=Tc, M=text_valid.shape[0])
 
+    # ------------------------------------------------------------------ CUDA graph of forward + backward
+    # The ~6 800 kernel launches of one headline step (140 per block) go through ctypes one by one; with a fixed
+    # geometry every pointer is static (engine._WS, the stash, grad_flat), so the whole forward + adapter backward can be
+    # captured once and replayed: cuda_graph=True / B200TTA_CUDA_GRAPH=1.  The optimizer stays outside the graph (the
+    # learning rate is a host argument of the AdamW kernel and changes during warm-up).  The first call with a new
+    # (shapes, adapter set) runs eagerly (workspace planning, stash sizing and the library's one-time attribute calls are
+    # not capturable), the second captures, later ones replay; inputs are copied into static buffers.
+    def _graph_key(self, cond, target, prompt_embeds, prompt_mask):
+        return (tuple(cond.shape), tuple(target.shape), tuple(prompt_embeds.shape),
+                None if prompt_mask is None else tuple(prompt_mask.shape), len(self.eng.lora_sites()))
+
+    def _forward_backward_graphed(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
+        key = self._graph_key(cond, target, prompt_embeds, prompt_mask)
+        st = self.__dict__.setdefault("_graph_state", {"key": None})
+        if st["key"] != key:
+            st.clear()
+            st.update(key=key, calls=0)
+        st["calls"] += 1
+        if st["calls"] == 1:
+            return self._forward_backward_eager(cond, target, prompt_embeds, prompt_mask, sigma, noise)
+        if st["calls"] == 2:
+            st["in"] = [t.clone() if t is not None else None for t in (cond, target, prompt_embeds, prompt_mask, sigma, noise)]
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                st["loss"] = self._forward_backward_eager(*st["in"])
+            st["graph"] = g
+        else:
+            for dst, src in zip(st["in"], (cond, target, prompt_embeds, prompt_mask, sigma, noise)):
+                if dst is not None:
+                    dst.copy_(src)
+        st["graph"].replay()
+        return st["loss"]
+
     def forward_backward(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
         """Loss (device scalar, f32) and adapter gradients for explicit (sigma, eps)."""
+        if self.cuda_graph and self.adapter is None and self.eng.bsa is None:
+            return self._forward_backward_graphed(cond, target, prompt_embeds, prompt_mask, sigma, noise)
+        return self._forward_backward_eager(cond, target, prompt_embeds, prompt_mask, sigma, noise)
+
+    def _forward_backward_eager(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
         eng = self.eng
         text_valid = eng.pack_text(prompt_embeds, prompt_mask)
         geo = self._geometry(cond, target, text_valid)

@@ -391,3 +391,31 @@ def test_deterministic_switch_gives_the_same_bits_every_run(setup, monkeypatch):
     rel = ((c.float() - a.float()).norm() / a.float().norm()).item()
     print(f"default (CTA-pair) GEMM vs deterministic GEMM forward: rel-L2 {rel:.3g}")
     assert rel < 5e-3
+
+
+def test_cuda_graph_replay_matches_eager(setup, monkeypatch):
+    """TTAStepper(cuda_graph=True): first step eager, second captured, later ones replayed from static input buffers --
+    same losses and the same post-step adapter parameters as the launch-by-launch path on identical draws."""
+    from longcat_video_tta_b200 import lora
+    from longcat_video_tta_b200.stepper import TTAStepper
+    s = setup
+    monkeypatch.setenv("B200TTA_DETERMINISTIC", "1")
+    cond, train, prompt = (s[k].to(BF16).cuda() for k in ("cond", "train", "prompt"))
+    mask = s["mask"].cuda()
+    draws = replay_draws(s["train"], 5)
+    out = {}
+    for mode in (False, True):
+        dit = s["B200DiT"].from_oracle(s["oracle"])
+        torch.manual_seed(7)
+        mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
+        st = TTAStepper(dit, cuda_graph=mode)
+        losses = [st.step(cond, train, prompt, mask, sg.cuda(), e.to(BF16).cuda(), lora._warmup_lr(2e-4, i, 3)).item()
+                  for i, (sg, e) in enumerate(draws)]
+        out[mode] = (losses, [p.detach().float().clone() for p in lora.get_lora_parameters(mods)])
+        if mode:
+            assert st._graph_state["calls"] == 5 and "graph" in st._graph_state
+    for a, b in zip(out[False][0], out[True][0]):
+        assert abs(a - b) <= 1e-5 * abs(a), (out[False][0], out[True][0])
+    worst = max(((a - b).norm() / (a.norm() + 1e-30)).item() for a, b in zip(out[False][1], out[True][1]))
+    print(f"cuda graph vs eager: losses {out[True][0]}, worst relative parameter difference {worst:.3g}")
+    assert worst < 1e-3
