@@ -58,7 +58,8 @@ typedef struct {
     const void* b_hi;
     int64_t k;
     int32_t b_mn_major;
-    int32_t reserved;
+    int32_t a_mn_major; /* A stored [K, M] (M contiguous); needs b_mn_major.  The weight-gradient form dW = dY^T X with
+                           dY [tokens, out], X [tokens, in] read in place (full-model TTA, run_full_tta.py:95-219) */
 } b200tta_gemm_seg;
 
 enum {

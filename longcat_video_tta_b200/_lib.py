@@ -20,7 +20,7 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 
 class GemmSeg(C.Structure):
     _fields_ = [("a", vp), ("lda", i64), ("b", vp), ("ldb", i64), ("b_hi", vp), ("k", i64),
-                ("b_mn_major", i32), ("reserved", i32)]
+                ("b_mn_major", i32), ("a_mn_major", i32)]
 
 
 class GemmEpi(C.Structure):

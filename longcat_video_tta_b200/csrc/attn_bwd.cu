@@ -235,12 +235,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_k128); tma_prefetch_desc(&p.tma_v128);
-        mbar_init(qdo_full, 2 * GROUP_THREADS);
+        mbar_init(qdo_full, 2 * GROUP_THREADS / 32);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
-        mbar_init(s_full, 1); mbar_init(s_free, 2 * GROUP_THREADS);
-        mbar_init(dp_full, 1); mbar_init(ds_full, 2 * GROUP_THREADS);
+        mbar_init(s_full, 1); mbar_init(s_free, 2 * GROUP_THREADS / 32);
+        mbar_init(dp_full, 1); mbar_init(ds_full, 2 * GROUP_THREADS / 32);
         mbar_init(dq_done, 1);
         fence_barrier_init();
     }
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             tmem_st_32x32b_x32(t_dq + lane_addr + c4 * 32, zero);   // every dQ MMA accumulates
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(qdo_full);
+            mbar_arrive_warp(qdo_full);
         }
         const float lse2 = row_ok ? p.LSE[(long long)head * p.n_q + q_row] * LOG2E : 0.f;
         const float dlt = row_ok ? p.delta[(long long)head * p.n_q + q_row] : 0.f;
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             tmem_ld_32x32b_x32(a_s, sv);
             tmem_ld_wait();
             tc_fence_before();
-            mbar_arrive(s_free);         // S(t + 1) may overwrite the buffer from here on
+            mbar_arrive_warp(s_free);         // S(t + 1) may overwrite the buffer from here on
             TL_DQ(warp == 3 && lane == 0, t, 1);     // S(t) loaded and released
             if (valid >= 32) {
 #pragma unroll
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dq_kernel(const __grid_constan
             tmem_st_32x32b_x16(a_dp, pk);   // dS over the first half of the dP columns this thread just loaded
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(ds_full);
+            mbar_arrive_warp(ds_full);
             TL_DQ(warp == 3 && lane == 0, t, 4);     // dS(t) stored and signalled
         }
         mbar_wait(dq_done, 0);
@@ -422,10 +422,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&s_full[b], 1); mbar_init(&dp_full[b], 1);
-            mbar_init(&p_full[b], GROUP_THREADS); mbar_init(&ds_full[b], GROUP_THREADS);
+            mbar_init(&p_full[b], GROUP_THREADS / 32); mbar_init(&ds_full[b], GROUP_THREADS / 32);
         }
         mbar_init(dkv_done, 2);
-        mbar_init(acc_zero, 2 * GROUP_THREADS);
+        mbar_init(acc_zero, 2 * GROUP_THREADS / 32);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             tmem_st_32x32b_x32(t_dk + lane_addr + (g * 2 + half) * 32, zero);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(acc_zero);
+            mbar_arrive_warp(acc_zero);
         }
         long long w_sdp = 0, w_pre = 0, w_math = 0, w_st = 0;
         [[maybe_unused]] const long long c_all0 = DBG_CLK();
@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             if (all_rows) exp_pass(std::false_type{}); else exp_pass(std::true_type{});
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_full[g]);                     // dV(u) can go while dS^T is still being computed
+            mbar_arrive_warp(&p_full[g]);                     // dV(u) can go while dS^T is still being computed
             long long c3 = DBG_CLK(); w_math += c3 - c2;
             TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 2);    // P^T(u) stored and signalled
             mbar_wait(&dp_full[g], (u >> 1) & 1);
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkv_kernel(const __grid_consta
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&ds_full[g]);
+            mbar_arrive_warp(&ds_full[g]);
             TL_DKV(half == 0 && quarter == 3 && lane == 0, u, 4);    // dS^T(u) stored and signalled
             w_st += DBG_CLK() - c3;
         });
@@ -767,9 +767,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&stat_full[i], 1); }
         mbar_init(do_full, 1); mbar_init(do_empty, 1);
         mbar_init(s_full, 1); mbar_init(dp_full, 1); mbar_init(dq_full, 1); mbar_init(ds_free, 1);
-        mbar_init(p_full, 2 * GROUP_THREADS); mbar_init(ds_full, 2 * GROUP_THREADS); mbar_init(dq_free, 2 * GROUP_THREADS);
+        mbar_init(p_full, 2 * GROUP_THREADS / 32); mbar_init(ds_full, 2 * GROUP_THREADS / 32); mbar_init(dq_free, 2 * GROUP_THREADS / 32);
         mbar_init(dkv_done, 1);
-        mbar_init(acc_zero, 2 * GROUP_THREADS);
+        mbar_init(acc_zero, 2 * GROUP_THREADS / 32);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
             tmem_st_32x32b_x32(t_dk + lane_addr + c4 * 32, zero);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(acc_zero);
+            mbar_arrive_warp(acc_zero);
         }
         // dS in shared memory as [q][key] (K-major B operand of dQ^T, MN-major A operand of dK): key `row` sits in half
         // (row >> 6), 16-byte chunk ((row & 63) >> 3) of the 128-byte row, swizzled with (q & 7).  Neighbouring lanes (keys
@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
             exp_half(0, s_cur, 1);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(p_full);
+            mbar_arrive_warp(p_full);
         }
         for (int t = 0; t < n_tiles; ++t) {
             const uint32_t par = (uint32_t)t & 1u;
@@ -1025,7 +1025,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
                     sts_b32(ds_thr + j * 256 + ((ds_cx ^ uint32_t((2 * j) & 7)) << 4), word);
                 }
                 fence_proxy_async();
-                mbar_arrive(ds_full);
+                mbar_arrive_warp(ds_full);
             }
             TL_F(tl, t, 4);                  // dS(t) stored and signalled
             // ---- second half of dQ^T(t-1): its first half's reduce-adds have had a dS phase to read the staging buffer
@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
                 tmem_ld_32x32b_x16(t_dp + lane_addr + c4 * 32 + 16, dqb);
                 tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(dq_free);                      // dP^T(t+1) may overwrite the columns
+                mbar_arrive_warp(dq_free);                      // dP^T(t+1) may overwrite the columns
                 stage(dqa, q0_cur, 0);
             }
             TL_F(tl, t, 7);                  // first half staged
@@ -1059,7 +1059,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) dkvq_kernel(const __grid_const
                 exp_half(tn & 1, s_nxt, 1);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive(p_full);
+                mbar_arrive_warp(p_full);
             }
             TL_F(tl, t, 2);                  // P^T(t+1) stored and signalled
             q0_prev = q0_cur;

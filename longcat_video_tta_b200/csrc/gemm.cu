@@ -48,6 +48,7 @@ struct alignas(64) GemmParams {
     CUtensorMap tma_b128[MAX_SEG];   // K-major B with a 128-row box: one CTA's half of the N tile in 2-CTA mode
     int k[MAX_SEG];
     int b_mn[MAX_SEG];
+    int a_mn[MAX_SEG];   // A stored [K, M] (M contiguous): weight gradients dW = dY^T X read dY [tokens, out] in place
     int has_hi[MAX_SEG];
     int nseg;
     int M, N;
@@ -233,7 +234,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                         uint8_t* sa = smem + stage * C::STAGE_BYTES;
                         uint8_t* sb = sa + C::A_BYTES;
                         mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                        tma_load_2d(sa, &p.tma_a[s], &full_bar[stage], kb * BK, m0);
+                        if (p.a_mn[s]) {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(sa + j * (64 * BK * 2), &p.tma_a[s], &full_bar[stage], m0 + j * 64, kb * BK);
+                        } else {
+                            tma_load_2d(sa, &p.tma_a[s], &full_bar[stage], kb * BK, m0);
+                        }
                         if (p.b_mn[s]) {
 #pragma unroll
                             for (int j = 0; j < BN / 64; ++j)
@@ -274,7 +281,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                         const int rem = p.k[s] - kb * BK;
                         const int ksteps = rem >= BK ? BK / 16 : (rem + 15) / 16;
                         const uint64_t ad = umma_desc_kmajor(sa);
-                        if (p.b_mn[s]) {
+                        if (p.a_mn[s]) {      // both operands token-major (dW = dY^T X): requires b_mn as well (host-checked)
+                            constexpr uint32_t idesc_mm = umma_idesc_bf16(BM, BN, 1, 1);
+                            const uint64_t am = umma_desc_mnmajor(sa, 64 * BK * 2), bd = umma_desc_mnmajor(sb, 64 * BK * 2);
+#pragma unroll
+                            for (int ks = 0; ks < BK / 16; ++ks) {
+                                if (ks < ksteps) {
+                                    umma_ss_e(d_tmem, umma_desc_advance(am, ks * 2048), umma_desc_advance(bd, ks * 2048), idesc_mm, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        } else if (p.b_mn[s]) {
                             const uint64_t bd = umma_desc_mnmajor(sb, 64 * BK * 2);
 #pragma unroll
                             for (int ks = 0; ks < BK / 16; ++ks) {
@@ -640,6 +657,7 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
     p.m_tiles = (int)((M + BM - 1) / BM);
     p.n_tiles = (int)((N + BN - 1) / BN);
     { const char* gm = getenv("B200TTA_GEMM_GROUP_M2"); p.group_m2 = gm ? atoi(gm) : 8; }
+    int any_a_mn = 0;
     for (int s = 0; s < nseg; ++s) {
         const b200tta_gemm_seg& g = segs[s];
         B200_REQUIRE(g.a && g.b && g.k > 0, "gemm: segment %d has null operand or k<=0", s);
@@ -648,10 +666,15 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
                      (long long)g.lda, (long long)g.ldb);
         p.k[s] = (int)g.k;
         p.b_mn[s] = g.b_mn_major ? 1 : 0;
+        p.a_mn[s] = g.a_mn_major ? 1 : 0;
+        any_a_mn |= p.a_mn[s];
+        B200_REQUIRE(!p.a_mn[s] || g.b_mn_major, "gemm: an MN-major A needs an MN-major B (weight-gradient form)");
         p.has_hi[s] = g.b_hi ? 1 : 0;
         B200_REQUIRE(!(g.b_hi && g.b_mn_major), "gemm: b_hi requires a K-major B");
         B200_REQUIRE(!g.b_hi || BN == 256, "gemm: b_hi requires 256-wide N tiles");
-        if (int rc = make_tmap_2d_bf16(&p.tma_a[s], g.a, (uint64_t)g.k, (uint64_t)M, (uint64_t)g.lda * 2, BK, BM)) return rc;
+        if (p.a_mn[s]) {
+            if (int rc = make_tmap_2d_bf16(&p.tma_a[s], g.a, (uint64_t)M, (uint64_t)g.k, (uint64_t)g.lda * 2, 64, BK)) return rc;
+        } else if (int rc = make_tmap_2d_bf16(&p.tma_a[s], g.a, (uint64_t)g.k, (uint64_t)M, (uint64_t)g.lda * 2, BK, BM)) return rc;
         if (g.b_mn_major) {
             if (int rc = make_tmap_2d_bf16(&p.tma_b[s], g.b, (uint64_t)N, (uint64_t)g.k, (uint64_t)g.ldb * 2, 64, BK)) return rc;
         } else if (g.b_hi) {
@@ -683,6 +706,6 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
     // 256-wide tiles run on CTA pairs with two free-running issuers (fastest; summation order over k-blocks not fixed run
     // to run).  B200TTA_DETERMINISTIC=1 (read per call) selects the single-issuer 1-CTA kernel: same bits every run.
     const char* det = getenv("B200TTA_DETERMINISTIC");
-    if (BN == 256 && !(det && det[0] == '1')) return launch2(p, st);
+    if (BN == 256 && !(det && det[0] == '1') && !any_a_mn) return launch2(p, st);   // MN-major A: 1-CTA kernel only
     return BN == 256 ? launch<256>(p, st) : launch<64>(p, st);
 }

@@ -51,6 +51,14 @@ __device__ __forceinline__ void fence_proxy_async() {  // generic-proxy writes -
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP (barrier initialised with the number of warps): 32 lanes arriving on one mbarrier serialise in the
+// shared-memory pipe (31 extra wavefronts per warp and hand-over; ncu counted them as 30-40 % of all shared-memory
+// wavefronts of the attention backward kernels).  __syncwarp orders the other lanes' earlier accesses (each lane issues
+// its own tcgen05 / proxy fences first) before lane 0's release-arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31u) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");

@@ -77,9 +77,11 @@ def epi(mode: int, d: torch.Tensor, *, bias: Optional[torch.Tensor] = None, d2=N
 
 def gemm(M: int, N: int, segs: Sequence[Tuple[torch.Tensor, torch.Tensor, int, bool, Optional[torch.Tensor]]],
          e: GemmEpi):
-    """segs: (A [M,K], B ([N,K] or [K,N] if mn_major), K, mn_major, B_hi or None)"""
+    """segs: (A [M,K], B ([N,K] or [K,N] if mn_major), K, mn_major, B_hi or None[, a_mn_major: A given as [K,M]])"""
     arr = (GemmSeg * len(segs))()
-    for i, (a, b, k, mn, b_hi) in enumerate(segs):
+    for i, seg in enumerate(segs):
+        a, b, k, mn, b_hi = seg[:5]
+        arr[i].a_mn_major = int(len(seg) > 5 and bool(seg[5]))
         _req(a, BF16, "gemm A")
         _req(b, BF16, "gemm B")
         arr[i].a, arr[i].lda = _p(a), _ld(a)

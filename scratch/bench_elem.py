@@ -23,5 +23,13 @@ t = timeit(lambda: ops.ln_mod_bwd(dx, g, x, mod[:, C:2 * C], dx_resid=dx, tokens
 print(f"ln_mod_bwd  {t*1e3:7.1f} us  {4 * N * C * 2 / t / 1e9:6.2f} TB/s (algorithmic 4 x N x C x 2 B)")
 t = timeit(lambda: ops.gate_mul(y, dx, mod[:, 2 * C:3 * C], tokens_per_frame=tpf))
 print(f"gate_mul    {t*1e3:7.1f} us  {2 * N * C * 2 / t / 1e9:6.2f} TB/s")
+H, D = 32, 128
+qkv = torch.randn(N, 3 * C, device="cuda").to(BF16); qk = torch.empty(N, 2 * C, dtype=BF16, device="cuda")
+dqk = torch.randn(N, 2 * C, device="cuda").to(BF16); dqkv = torch.empty(N, 3 * C, dtype=BF16, device="cuda")
+wq = torch.ones(D, dtype=BF16, device="cuda"); wk = torch.ones(D, dtype=BF16, device="cuda")
+t = timeit(lambda: ops.qk_rmsnorm_rope_fwd(qk, qkv, wq, wk, H, H, grid_hw=(30, 52), rope_base=10000.0))
+print(f"qk_rope_fwd {t*1e3:7.1f} us  {4 * N * C * 2 / t / 1e9:6.2f} TB/s (algorithmic 4 x N x C x 2 B: q, k in and out)")
+t = timeit(lambda: ops.qk_rmsnorm_rope_bwd(dqkv, dqk, qkv, wq, wk, H, H, grid_hw=(30, 52), rope_base=10000.0))
+print(f"qk_rope_bwd {t*1e3:7.1f} us  {6 * N * C * 2 / t / 1e9:6.2f} TB/s (algorithmic 6 x N x C x 2 B: dq, dk, q, k in; dq, dk out)")
 t = timeit(lambda: y.copy_(x))
 print(f"torch copy  {t*1e3:7.1f} us  {2 * N * C * 2 / t / 1e9:6.2f} TB/s")

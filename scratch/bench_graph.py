@@ -15,13 +15,15 @@ else:
     dit = B200DiT.random_init("13.6b", seed=0, device=dev)
     Tc, Tt, Hl, Wl, Cc, steps = 4, 20, 60, 104, 4096, 3
 torch.manual_seed(7)
-lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
+mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
 g = torch.Generator().manual_seed(1)
 cond = torch.randn(1, 16, Tc, Hl, Wl, generator=g).to(BF16).to(dev)
 train = torch.randn(1, 16, Tt, Hl, Wl, generator=g).to(BF16).to(dev)
 prompt = torch.randn(1, 1, 512, Cc, generator=g).to(BF16).to(dev)
 mask = torch.ones(1, 512, dtype=torch.int64, device=dev)
 for mode in (False, True):
+    torch.manual_seed(7)
+    lora.reset_lora_weights(mods)        # both modes start from the same adapters
     st = TTAStepper(dit, cuda_graph=mode)
     sigma = torch.full((1,), 0.4, device=dev)
     noise = torch.randn_like(train)

@@ -51,6 +51,23 @@ def test_gemm_plain(ops, M, N, K, mn):
     close(d, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (512, 512, 1000), (1536, 512, 1024), (64, 4096, 3120), (4096, 64, 1024),
+                                   (12288, 4096, 4680)])
+def test_gemm_weight_gradient_form(ops, M, N, K):
+    """dW [out, in] = dY^T X with dY [tokens, out] and X [tokens, in] read in place (both operands token-major): the
+    product full-model TTA needs for every linear (run_full_tta.py:95-219 lets autograd form it)."""
+    dy = rnd(K, M, scale=0.5, seed=3)
+    x = rnd(K, N, scale=0.5, seed=4)
+    dw = torch.empty(M, N, dtype=BF16, device="cuda")
+    ops.gemm(M, N, [(dy, x, K, True, None, True)], ops.epi(ops.EPI_STORE, dw))
+    close(dw, dy.float().t() @ x.float())
+    # fp32 output, strided token-major views (a column slice of a fused buffer, as qkv / kv gradients are)
+    big = rnd(K, M + 64, scale=0.5, seed=5)
+    dwf = torch.empty(M, N, dtype=F32, device="cuda")
+    ops.gemm(M, N, [(big[:, 64:], x, K, True, None, True)], ops.epi(ops.EPI_STORE_F32, dwf))
+    close(dwf, big[:, 64:].float().t() @ x.float())
+
+
 def test_gemm_two_segments_lora_and_bias_f32_out(ops):
     M, N, K, r = 1000, 768, 512, 16
     x, w = rnd(M, K, seed=1), rnd(N, K, scale=0.05, seed=2)
