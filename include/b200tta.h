@@ -308,6 +308,15 @@ int b200tta_mt_adamw(const b200tta_tensor_desc* descs_dev, int32_t n, int64_t ma
                      float grad_scale, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                      int32_t faithful_bf16, b200tta_stream_t stream);
 
+/* torch.optim.SGD(momentum=0, weight_decay=wd) over the same descriptor table (full-model TTA default optimizer,
+ * lora_experiment/scripts/run_full_tta.py:132-138): g = coef * grad_scale * grad + wd * p ; p -= lr * g. */
+int b200tta_mt_sgd(const b200tta_tensor_desc* descs_dev, int32_t n, int64_t max_numel, const float* coef, float grad_scale,
+                   float lr, float weight_decay, b200tta_stream_t stream);
+
+/* out[c] = sum over rows of A[row, c]  (bf16 in, f32 out; bias gradients of full-model TTA). */
+int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t rows, int32_t C, b200tta_stream_t stream);
+
+
 #ifdef __cplusplus
 }
 #endif

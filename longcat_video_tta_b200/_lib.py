@@ -78,6 +78,8 @@ SIGNATURES = {
     "b200tta_mt_sumsq": [vp, i32, i64, vp, vp],
     "b200tta_clip_coef": [vp, vp, vp, i32, f32, i32, f32, vp],
     "b200tta_mt_adamw": [vp, i32, i64, vp, f32, f32, f32, f32, f32, f32, i32, i32, vp],
+    "b200tta_mt_sgd": [vp, i32, i64, vp, f32, f32, f32, vp],
+    "b200tta_colsum": [vp, vp, i64, i64, i32, vp],
 }
 
 _lib = None

@@ -790,6 +790,18 @@ extern "C" int b200tta_gate_mul(void* dY, int64_t lddy, const void* dX, int64_t 
     return B200TTA_OK;
 }
 
+extern "C" int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t rows, int32_t C, b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(out && A && rows > 0 && C > 0, "colsum: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    B200_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
+    const int rpb = 256;
+    dim3 g((C + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
+    colsum_prod_kernel<<<g, 256, 0, st>>>(out, 0, (const __nv_bfloat16*)A, lda, nullptr, 0, rows, C, (int)(rows > 2147483647ll ? 2147483647ll : rows), rpb);
+    B200_LAUNCHED();
+    return B200TTA_OK;
+}
+
 extern "C" int b200tta_noise_patchify(void* P, float* V, float* timestep, const void* cond, const void* target,
                                       const void* noise, const float* sigma, int32_t t_cond, int32_t t_tgt, int32_t H,
                                       int32_t W, float num_train_timesteps, b200tta_stream_t stream) {

@@ -123,10 +123,27 @@ __global__ void __launch_bounds__(OPT_THREADS) adamw_kernel(const b200tta_tensor
     }
 }
 
+// plain SGD as torch.optim.SGD(momentum=0) computes it (run_full_tta.py:132-138): g += wd * p ; p -= lr * g
+__global__ void __launch_bounds__(OPT_THREADS) sgd_kernel(const b200tta_tensor_desc* __restrict__ descs,
+                                                          const float* __restrict__ coef, float grad_scale, float lr, float wd) {
+    const b200tta_tensor_desc d = descs[blockIdx.y];
+    const float c = (coef ? coef[blockIdx.y] : 1.0f) * grad_scale;
+    for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < d.numel; i += (long long)gridDim.x * OPT_THREADS) {
+        float p = d.master ? d.master[i]
+                           : (d.is_bf16 ? __bfloat162float(reinterpret_cast<__nv_bfloat16*>(d.param)[i])
+                                        : reinterpret_cast<float*>(d.param)[i]);
+        const float g = grad_at(d, i) * c + wd * p;
+        p -= lr * g;
+        if (d.master) d.master[i] = p;
+        if (d.is_bf16) reinterpret_cast<__nv_bfloat16*>(d.param)[i] = __float2bfloat16(p);
+        else reinterpret_cast<float*>(d.param)[i] = p;
+    }
+}
+
 inline dim3 opt_grid(int n, long long max_numel) {
     long long gx = (max_numel + OPT_CHUNK - 1) / OPT_CHUNK;
     if (gx < 1) gx = 1;
-    if (gx > 64) gx = 64;
+    if (gx > 512) gx = 512;      // (full-model TTA: tensors of up to 135 M elements)
     return dim3((unsigned)gx, (unsigned)n);
 }
 
@@ -164,6 +181,15 @@ extern "C" int b200tta_mt_adamw(const b200tta_tensor_desc* descs_dev, int32_t n,
     a.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     a.faithful_bf16 = faithful_bf16;
     adamw_kernel<<<opt_grid(n, max_numel), OPT_THREADS, 0, (cudaStream_t)stream>>>(descs_dev, coef, a);
+    B200_LAUNCHED();
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_mt_sgd(const b200tta_tensor_desc* descs_dev, int32_t n, int64_t max_numel, const float* coef,
+                              float grad_scale, float lr, float weight_decay, b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(descs_dev && n > 0 && n <= 65535 && max_numel > 0, "mt_sgd: bad arguments (n=%d)", n);
+    sgd_kernel<<<opt_grid(n, max_numel), OPT_THREADS, 0, (cudaStream_t)stream>>>(descs_dev, coef, grad_scale, lr, weight_decay);
     B200_LAUNCHED();
     return B200TTA_OK;
 }

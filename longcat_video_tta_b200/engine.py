@@ -239,6 +239,35 @@ class _Range:
         return False
 
 
+# ---------------------------------------------------------------------------------------------------- full-model gradients
+class FullGrads:
+    """fp32 gradients of EVERY DiT parameter in one flat buffer (full-model TTA, lora_experiment/scripts/run_full_tta.py:95-219
+    lets autograd produce them; here the engine's backward additionally forms dW = dY^T X / db = colsum(dY) for every
+    linear it walks through, plus the norm / adaLN / embedder gradients).  One flat buffer = one all-reduce payload."""
+
+    def __init__(self, dit):
+        self.params: List[nn.Parameter] = [p for p in dit.parameters()]
+        self.names = [n for n, _ in dit.named_parameters()]
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=F32, device=dev)
+        self._by_id: Dict[int, torch.Tensor] = {}
+        off = 0
+        for p in self.params:
+            self._by_id[id(p)] = self.flat[off: off + p.numel()].view(p.shape)
+            off += p.numel()
+
+    def g(self, p) -> torch.Tensor:
+        return self._by_id[id(p)]
+
+    def named(self):
+        return {n: self._by_id[id(p)] for n, p in zip(self.names, self.params)}
+
+
+def _silu(x):
+    return x * torch.sigmoid(x)
+
+
 # ---------------------------------------------------------------------------------------------------- engine
 class TTAEngine:
     def __init__(self, dit):
@@ -257,6 +286,7 @@ class TTAEngine:
         # block-sparse self-attention (720p refinement stage, configs[4]): see bsa.py for the definition
         self.bsa = dict(sparsity=float(cfgb.get("sparsity", 0.9375)), chunk=tuple(cfgb.get("chunk", (4, 4, 8)))) \
             if getattr(cfg, "enable_bsa", False) else None
+        self.full: Optional[FullGrads] = None   # full-model TTA: gradients for every parameter (enable_full_grads)
         self._stash = None          # activation stash of the training geometry (see _ensure_stash)
         self._stash_on = False      # the forward in flight writes / the recompute reads the stash
         self.device = dit.x_embedder.proj.weight.device
@@ -307,6 +337,29 @@ class TTAEngine:
     def adapter_parameters(self) -> List[nn.Parameter]:
         self.resolve_sites()
         return [p for s in self.lora_sites() for p in s.params]
+
+    # ------------------------------------------------------------------ full-model gradients
+    def enable_full_grads(self) -> FullGrads:
+        if self.full is None:
+            self._release_stash()
+            self.full = FullGrads(self.dit)
+        return self.full
+
+    def disable_full_grads(self):
+        self.full = None
+
+    def _wgrad(self, W: torch.Tensor, bias: Optional[torch.Tensor], dy: torch.Tensor, x: torch.Tensor):
+        """dW [out, in] = dY^T X and db = colsum(dY), fp32, with dY [tokens, out] and X [tokens, in] read in place."""
+        out_f, in_f = W.shape[0], W.numel() // W.shape[0]
+        gw = self.full.g(W).view(out_f, in_f)
+        ops.gemm(out_f, in_f, [(dy, x, dy.shape[0], True, None, True)], ops.epi(ops.EPI_STORE_F32, gw))
+        if bias is not None:
+            ops.colsum(self.full.g(bias), dy)
+
+    def _modulation_grads(self, lin: nn.Linear, t_in: torch.Tensor, dmod: torch.Tensor):
+        """adaLN linear  mod = silu(t) W^T + b  with T (= latent frames) rows: tiny fp32 products"""
+        self.full.g(lin.weight).copy_(dmod.t() @ _silu(t_in))
+        self.full.g(lin.bias).copy_(dmod.sum(0))
 
     # ------------------------------------------------------------------ workspace
     def plan(self, geo: Geometry):
@@ -366,6 +419,8 @@ class TTAEngine:
         ws.dpred = e(max(Nn, 1), 64)
         ws.loss = torch.zeros(1, dtype=F32, device=dev)
         ws.dmod, ws.dmodf, ws.dt = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32), e(T, self.Ct, dt=F32)
+        ws.dt_total = e(T, self.Ct, dt=F32)      # full-model TTA: d loss / d(timestep embedding), summed over its users
+        ws.d_y = e(M, C)                         # full-model TTA: d loss / d(text rows), summed over the blocks
         ws.branch_a = ws.branch_m = None  # branch outputs, allocated on demand (FiLM / delta gate gradients)
         if self.bsa is not None:
             from . import bsa as _bsa
@@ -446,6 +501,8 @@ class TTAEngine:
         return self.ws.xa[nm].view(-1)[: rows * s.r].view(rows, s.r)
 
     def _linear_bwd(self, s: LinearSite, dy, x, e, nm):
+        if self.full is not None:
+            self._wgrad(s.W, s.bias, dy, x)
         if s.has_lora:
             rows = dy.shape[0]
             u = self.ws.u.view(-1)[: rows * s.r].view(rows, s.r)
@@ -595,8 +652,9 @@ class TTAEngine:
         s1, s3, s2 = st["w1"], st["w3"], st["w2"]
         # the recompute pass never needs the block output (xs[b+1] is kept): w2 only re-runs for its own LoRA / FiLM needs
         need_w2 = (not recompute) or keep_branch or s2.has_lora
+        need_h = need_w2 or self.full is not None      # full-model TTA: dW of w2 needs its input h = silu(h1) h3
         h_stashed = recompute and self._stashed(b, "h")
-        if not h_stashed or s1.has_lora or s3.has_lora:
+        if not h_stashed or s1.has_lora or s3.has_lora or self.full is not None:
             ops.ln_mod_fwd(ws.xm2, ws.x2, scale_mlp, shift_mlp, tokens_per_frame=tpf)
         if s1.has_lora or s3.has_lora:
             if h_stashed:
@@ -605,11 +663,11 @@ class TTAEngine:
             else:
                 self._linear_fwd_xa(s1, ws.xm2, ops.epi(ops.EPI_STORE, ws.h1), "w1")
                 self._linear_fwd_xa(s3, ws.xm2, ops.epi(ops.EPI_STORE, ws.h3), "w3")
-            if need_w2:
+            if need_h:
                 ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
         elif not h_stashed:
             ops.lora_linear_fwd(ws.xm2, s1.W, ops.epi(ops.EPI_SWIGLU, ws.h, d2=ws.h1, d3=ws.h3), W_hi=s3.W)
-        elif need_w2:
+        elif need_h:
             ops.swiglu_fwd(ws.h, ws.h1, ws.h3)
         if need_w2:
             self._linear_fwd_xa(s2, ws.h, ops.epi(ops.EPI_GATE_RESID, x_out, resid=ws.x2, gate=gate_mlp, tokens_per_frame=tpf,
@@ -771,6 +829,9 @@ class TTAEngine:
             self._linear_bwd(s2, ws.g1, ws.h, ops.epi(ops.EPI_SWIGLU_BWD, ws.dh1, d2=ws.dh3, aux1=ws.h1, aux2=ws.h3), "w2")
             ops.gemm(N, C, [(ws.dh1, s1.W, self.F, True, None), (ws.dh3, s3.W, self.F, True, None)],
                      ops.epi(ops.EPI_STORE, ws.g2))
+            if self.full is not None:
+                self._wgrad(s1.W, s1.bias, ws.dh1, ws.xm2)
+                self._wgrad(s3.W, s3.bias, ws.dh3, ws.xm2)
         tap(b, "ffn_gin", ws.g2)
         ops.ln_mod_bwd(dx, ws.g2, ws.x2, scale_mlp, dx_resid=dx, tokens_per_frame=tpf,
                        dscale_acc=dmod[:, 4 * C:5 * C] if want_mod else None,
@@ -792,7 +853,10 @@ class TTAEngine:
                                     dwq_acc=self._ngrad(ex, b, "cross_attn.q_norm.weight", cq) if ng else None)
             ops.qk_rmsnorm_rope_bwd(ws.dkvc[:, :C], ws.dkvc[:, :C], ws.kvc[:, :C], ck, None, H, 0, rope=False,
                                     dwq_acc=self._ngrad(ex, b, "cross_attn.k_norm.weight", ck) if ng else None)
-            self._linear_bwd(st["kv_linear"], ws.dkvc, ws.y, None, "kv_linear")                    # adapter grads only
+            if self.full is not None:     # the text embedder trains too: d y accumulates over the blocks (resid = running sum)
+                self._linear_bwd(st["kv_linear"], ws.dkvc, ws.y, ops.epi(ops.EPI_GATE_RESID, ws.d_y, resid=ws.d_y), "kv_linear")
+            else:
+                self._linear_bwd(st["kv_linear"], ws.dkvc, ws.y, None, "kv_linear")                # adapter grads only
             s = st["q_linear"]
             self._linear_bwd(s, ws.dqc, ws.xn, ops.epi(ops.EPI_STORE, ws.g2[:Nn]), "q_linear")    # d xn
             tap(b, "cross_gin", ws.g2[:Nn])
@@ -836,6 +900,9 @@ class TTAEngine:
                 ada = blk.adaLN_modulation[1]
                 ops.skinny_linear_bwd(ws.dt, dmod, self._t_for_block(b, ex), ada.weight, act=1)
                 ex.d_t[b] = ws.dt.clone()
+            if self.full is not None:
+                self._modulation_grads(blk.adaLN_modulation[1], self._t_for_block(b, ex), dmod)
+                ws.dt_total.add_(ws.dt)
 
     def _tap(self, b: int, name: str, t: torch.Tensor):
         """debug hook: engine.debug = {} collects clones of backward intermediates (tests only)"""
@@ -923,6 +990,15 @@ class TTAEngine:
         if ex is not None:
             for v in ex.d_norm.values():
                 v.zero_()
+        full = self.full
+        if full is not None:
+            if ex is None or not (ex.need_dmod and ex.need_dt and ex.norm_grads):
+                raise RuntimeError("full-model gradients need Extras(need_dmod, need_dt, norm_grads) -- use TTAStepper(full=True)")
+            full.flat.zero_()
+            ws.dt_total.zero_()
+            ws.d_y.zero_()
+            # final linear: dW [64, C] = dpred^T xf (noised rows), db = colsum(dpred)
+            self._wgrad(fl.linear.weight, fl.linear.bias, ws.dpred, ws.xf[geo.Nc:])
         # final layer: d xf = dpred W_lin ; context rows are zero
         ws.g1[: geo.Nc].zero_()
         ops.gemm(geo.Nn, C, [(ws.dpred, fl.linear.weight, 64, True, None)], ops.epi(ops.EPI_STORE, ws.g1[geo.Nc:]))
@@ -937,6 +1013,9 @@ class TTAEngine:
                 t_f = torch.add(ws.t, ex.t_offset_final.to(F32)[None, :], out=ws.t_blk)
             ops.skinny_linear_bwd(ws.dt, ws.dmodf, t_f, fl.adaLN_modulation[1].weight, act=1)
             ex.d_t_final = ws.dt.clone()
+            if full is not None:
+                self._modulation_grads(fl.adaLN_modulation[1], t_f, ws.dmodf)
+                ws.dt_total.add_(ws.dt)
         if ex is not None and ex.hidden_final is not None:
             ex.d_hidden_final = ws.dx.float().sum(0)
         for b in reversed(range(self.L)):
@@ -945,8 +1024,50 @@ class TTAEngine:
                     self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
             with _Range(f"bwd.block{b}"):
                 self._block_bwd(b, ws.xs[b], ex)
+        if full is not None:
+            self._embedder_grads(ex)
         self._ws_holds = None
         self._stash_on = False
+
+    def _embedder_grads(self, ex: Extras):
+        """full-model TTA: what is left after the block loop -- norm weights, patch / timestep / text embedders.
+        ws.dx holds d loss / d(patch-embedder output); the small fp32 pieces (T or M rows) are plain tensor algebra."""
+        ws, geo, C, full, dit = self.ws, self.geo, self.C, self.full, self.dit
+        named = full.named()
+        for key, g in ex.d_norm.items():                       # pre_crs_attn_norm (w, b), q / k RMSNorm weights
+            named[key].copy_(g.view(named[key].shape))
+        # patch embedder: x0 = P W^T + b with W [C, 64] (Conv3d weight flattened in P's column order)
+        pe = dit.x_embedder.proj
+        gw = full.g(pe.weight).view(C, 64)
+        ops.gemm(C, 64, [(ws.dx, ws.P, geo.N, True, None, True)], ops.epi(ops.EPI_STORE_F32, gw))
+        ops.colsum(full.g(pe.bias), ws.dx)
+        # timestep embedder: t = W2 silu(W0 f + b0) + b2, T rows, fp32
+        te, dt = dit.t_embedder, ws.dt_total
+        w0, w2 = te.mlp[0], te.mlp[2]
+        full.g(w2.weight).copy_(dt.t() @ _silu(ws.th))
+        full.g(w2.bias).copy_(dt.sum(0))
+        sg = torch.sigmoid(ws.th)
+        d_th = (dt @ w2.weight.float()) * (sg * (1.0 + ws.th * (1.0 - sg)))
+        full.g(w0.weight).copy_(d_th.t() @ ws.tfeat)
+        full.g(w0.bias).copy_(d_th.sum(0))
+        # text embedder: y = (gelu_tanh(text W0^T + b0) W2^T + b2) * keep
+        ye = dit.y_embedder.y_proj
+        text = self._text_cache[4]
+        d_y = ws.d_y
+        if getattr(self, "_text_keep", None) is not None:
+            d_y.mul_(self._text_keep)
+        M = text.shape[0]
+        self._wgrad(ye[2].weight, ye[2].bias, d_y, ws.y1)
+        d_y1 = torch.empty(M, C, dtype=BF16, device=self.device)
+        ops.lora_linear_bwd(d_y, ye[2].weight, ops.epi(ops.EPI_STORE, d_y1))
+        pre = torch.empty(M, C, dtype=BF16, device=self.device)
+        ops.gemm(M, C, [(text, ye[0].weight, text.shape[1], False, None)], ops.epi(ops.EPI_STORE, pre, bias=ye[0].bias))
+        u = pre.float()
+        k0, k1 = 0.7978845608028654, 0.044715
+        th = torch.tanh(k0 * (u + k1 * u ** 3))
+        dgelu = 0.5 * (1.0 + th) + 0.5 * u * (1.0 - th * th) * k0 * (1.0 + 3.0 * k1 * u * u)
+        d_pre = (d_y1.float() * dgelu).to(BF16)
+        self._wgrad(ye[0].weight, ye[0].bias, d_pre, text)
 
     # ------------------------------------------------------------------ step-level helpers
     def set_inputs(self, cond, target, noise, sigma):

@@ -281,6 +281,12 @@ def lora_grad(G, P, Q):
     _call("b200tta_lora_grad", _p(G), _p(P), _ld(P), _p(Q), _ld(Q), n_tok, m, r, _stream())
 
 
+def colsum(out, a):
+    """out [C] f32 = column sums of a [rows, C] bf16 (row stride arbitrary)"""
+    rows, Cdim = a.shape
+    _call("b200tta_colsum", _p(out), _p(a), _ld(a), rows, Cdim, _stream())
+
+
 # ------------------------------------------------------------------------------------------------ optimizer
 class TensorList:
     """Device-resident descriptor table over the adapter tensors (one multi-tensor launch covers them all)."""
@@ -294,8 +300,8 @@ class TensorList:
             arr[i].param = _p(p)
             arr[i].master = _p(e.get("master"))
             arr[i].grad = _p(e["grad"])
-            arr[i].exp_avg = _p(e["exp_avg"])
-            arr[i].exp_avg_sq = _p(e["exp_avg_sq"])
+            arr[i].exp_avg = _p(e.get("exp_avg"))
+            arr[i].exp_avg_sq = _p(e.get("exp_avg_sq"))
             arr[i].numel = p.numel()
             arr[i].is_bf16 = int(p.dtype == BF16)
             tr = e.get("grad_transposed", False)
@@ -314,6 +320,10 @@ class TensorList:
         _call("b200tta_mt_sumsq", _p(self.dev), self.n, self.max_numel, _p(self.sumsq), _stream())
         _call("b200tta_clip_coef", _p(self.coef), _p(self.total_norm), _p(self.sumsq), self.n, float(max_norm),
               int(per_tensor), float(grad_scale), _stream())
+
+    def sgd(self, *, lr, weight_decay=0.01, grad_scale: float = 1.0, use_coef: bool = True):
+        _call("b200tta_mt_sgd", _p(self.dev), self.n, self.max_numel, _p(self.coef) if use_coef else None, float(grad_scale),
+              float(lr), float(weight_decay), _stream())
 
     def adamw(self, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step: int, grad_scale: float = 1.0,
               use_coef: bool = True, faithful_bf16: bool = False):

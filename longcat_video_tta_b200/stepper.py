@@ -38,12 +38,17 @@ class TTAStepper:
     def __init__(self, dit, *, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01,
                  max_grad_norm: float = 1.0, per_tensor_clip: bool = False, master_weights: bool = True,
                  faithful_bf16: bool = False, adapter=None, train_lora: bool = True, build_optimizer: bool = True,
-                 process_group=None, cuda_graph: Optional[bool] = None):
+                 process_group=None, cuda_graph: Optional[bool] = None, full: bool = False, optimizer: str = "adamw"):
         """
         master_weights : keep an fp32 master copy (and fp32 Adam moments) of every bf16 adapter tensor.  The
                          reference keeps params and moments in bf16 (run_lora_tta.py:332) where updates below half an
                          ulp are lost; ``faithful_bf16=True, master_weights=False`` reproduces
                          that op-by-op rounding instead.
+        full           : full-model TTA (lora_experiment/scripts/run_full_tta.py:95-219): EVERY parameter of the DiT trains.
+                         The engine's backward then also forms the weight / bias / norm / embedder gradients (fp32, one
+                         flat buffer = the all-reduce payload); parameters stay bf16 without fp32 masters (13.6 B masters
+                         would not fit next to the gradients), the update is computed in fp32 and rounded once.
+        optimizer      : "adamw" | "sgd" (torch.optim.SGD(momentum=0) semantics; the reference's default for full TTA)
         adapter        : one of adapters.{DeltaA,DeltaB,DeltaC,NormTuneForward,FiLMAdapter}Wrapper: supplies the non-LoRA
                          trainables (``trainable()``), where they enter the network (``build_extras()``) and their
                          fp32 gradients after the backward (``grads_from(extras)``).
@@ -81,6 +86,23 @@ class TTAStepper:
                     entries.append(e)
                 if s.staged:
                     self._staged.append((s, entries[-len(s.params):]))
+        self.full = bool(full)
+        self.optimizer = optimizer
+        if optimizer not in ("adamw", "sgd"):
+            raise ValueError(f"unknown optimizer {optimizer!r}")
+        self._full_extras = None
+        if self.full:
+            if adapter is not None or self.eng.lora_sites():
+                raise ValueError("full-model TTA runs on a plain DiT (no LoRA injection, no adapter wrapper)")
+            fg = self.eng.enable_full_grads()
+            entries = []
+            for p in fg.params:
+                e = dict(param=p.data, grad=fg.g(p))
+                if optimizer == "adamw":   # states in the parameter dtype, as torch.optim.AdamW keeps them
+                    e["exp_avg"], e["exp_avg_sq"] = torch.zeros_like(p.data), torch.zeros_like(p.data)
+                else:
+                    e["exp_avg"] = e["exp_avg_sq"] = None
+                entries.append(e)
         self._n_lora_entries = len(entries)
         self._extra_entries = []
         for p in self.extra_params:
@@ -139,15 +161,20 @@ class TTAStepper:
 
     def forward_backward(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
         """Loss (device scalar, f32) and adapter gradients for explicit (sigma, eps)."""
-        if self.cuda_graph and self.adapter is None and self.eng.bsa is None:
+        if self.cuda_graph and self.adapter is None and self.eng.bsa is None and not self.full:
             return self._forward_backward_graphed(cond, target, prompt_embeds, prompt_mask, sigma, noise)
         return self._forward_backward_eager(cond, target, prompt_embeds, prompt_mask, sigma, noise)
 
+    @torch.no_grad()      # the engine IS the backward: nothing here may be recorded by autograd (parameters may require grad)
     def _forward_backward_eager(self, cond, target, prompt_embeds, prompt_mask, sigma, noise) -> torch.Tensor:
         eng = self.eng
         text_valid = eng.pack_text(prompt_embeds, prompt_mask)
         geo = self._geometry(cond, target, text_valid)
         ex = self.extras = self.adapter.build_extras() if self.adapter is not None else None
+        if self.full:
+            from .engine import Extras
+            ex = self.extras = Extras(eng.L)
+            ex.need_dmod = ex.need_dt = ex.norm_grads = True
         eng._prepare(geo, ex)
         eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
         eng.forward_tokens(text_valid, ex, stash=True)
@@ -167,7 +194,10 @@ class TTAStepper:
     def _sync_grads(self):
         if self.world > 1:
             from .dist import all_reduce_grads
-            bufs = ([self.eng.grad_flat] if self._n_lora_entries else []) + [e["grad"] for e in self._extra_entries]
+            if self.full:
+                bufs = [self.eng.full.flat]
+            else:
+                bufs = ([self.eng.grad_flat] if self._n_lora_entries else []) + [e["grad"] for e in self._extra_entries]
             all_reduce_grads(bufs, self.pg)
 
     def optimizer_step(self, lr: float):
@@ -183,8 +213,12 @@ class TTAStepper:
         gs = 1.0 / self.world
         if self.max_norm is not None and self.max_norm > 0:
             tl.clip_coef(self.max_norm, per_tensor=self.group.per_tensor_clip, grad_scale=gs)
-        tl.adamw(lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, step=self.step_count, grad_scale=gs,
-                 use_coef=self.max_norm is not None and self.max_norm > 0, faithful_bf16=self.faithful)
+        use_coef = self.max_norm is not None and self.max_norm > 0
+        if self.optimizer == "sgd":
+            tl.sgd(lr=lr, weight_decay=self.wd, grad_scale=gs, use_coef=use_coef)
+        else:
+            tl.adamw(lr=lr, betas=self.betas, eps=self.eps, weight_decay=self.wd, step=self.step_count, grad_scale=gs,
+                     use_coef=use_coef, faithful_bf16=self.faithful)
 
     def step(self, cond, target, prompt_embeds, prompt_mask, sigma, noise, lr: float) -> torch.Tensor:
         loss = self.forward_backward(cond, target, prompt_embeds, prompt_mask, sigma, noise)
