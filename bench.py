@@ -38,6 +38,7 @@ METHOD_NAMES = {
     "delta_c": "delta-C (16-channel output bias; forward only)",
     "norm_tune": "norm-tune all_norm (LN affine + q/k RMSNorm weights, 417 792 params)",
     "film": "FiLM full (4 groups x [6C] additive adaLN corrections)",
+    "full": "full-model TTA (all 13.6 B parameters, SGD momentum 0; SURVEY 8f row 3)",
 }
 
 
@@ -391,6 +392,9 @@ def run_b200(args):
     if args.method == "lora":
         with contextlib.redirect_stdout(sys.stderr):  # stdout carries exactly one JSON line
             mods = lora.inject_lora_into_dit(dit, rank=16, alpha=32.0, target_modules=["qkv", "proj"])
+    elif args.method == "full":
+        mods = None
+        dit.requires_grad_(True)
     else:   # BASELINE.json configs[2]: the delta / norm / AdaLN(FiLM) / bias families (SURVEY 8d "Config 3")
         from longcat_video_tta_b200 import adapters
         C, Ct = cfg.hidden_size, cfg.adaln_tembed_dim
@@ -412,14 +416,16 @@ def run_b200(args):
     mask_h = torch.ones(1, M, dtype=torch.int64).pin_memory()
     cond, train, prompt, mask = (t.to(dev) for t in (cond_h, train_h, prompt_h, mask_h))
     torch.manual_seed(42 + rank)
-    if wrapper is None:
+    if args.method == "full":   # run_full_tta.py defaults: SGD(momentum 0), lr 1e-5, warm-up 2, wd 0.01, clip 1.0
+        stepper = TTAStepper(dit, full=True, optimizer="sgd", weight_decay=0.01, max_grad_norm=1.0)
+    elif wrapper is None:
         stepper = TTAStepper(dit, eps=1e-8, weight_decay=0.01, max_grad_norm=1.0, master_weights=True)
     else:   # adapters._optimize: AdamW eps 1e-15, wd 0.01, constant lr 1e-3, clip 1.0 (per tensor for delta-B)
         stepper = TTAStepper(dit, adapter=wrapper, train_lora=False, eps=1e-15, weight_decay=0.01, max_grad_norm=1.0,
                              per_tensor_clip=wrapper.per_tensor_clip)
 
     def one_step(c, t, p, m, i):
-        lr = lora._warmup_lr(2e-4, i, 3) if wrapper is None else 1e-3
+        lr = lora._warmup_lr(1e-5, i, 2) if args.method == "full" else (lora._warmup_lr(2e-4, i, 3) if wrapper is None else 1e-3)
         sigma = torch.rand(1, device=dev, dtype=torch.float32) * 0.999 + 0.001
         noise = torch.randn_like(t)
         return stepper.step(c, t, p, m, sigma, noise, lr)
@@ -479,6 +485,8 @@ def run_b200(args):
     geo = dit.engine.geo
     work = f_alg(cfg.hidden_size, cfg.ffn_dim, cfg.depth, geo.N, geo.Nc, geo.M, 16 if args.method == "lora" else 0,
                  lora_sites_qkv_proj)
+    if args.method == "full":       # + one weight-gradient GEMM per linear: forward, dX and dW
+        work["total"] = 3 * work["f_lin"] + 3.5 * (work["f_attn"] + work["f_x"])
     if args.method == "delta_c":    # output-bias only: the gradient is a reduction of d loss / d pred, forward only
         work["total"] = work["f_lin"] + work["f_attn"] + work["f_x"]
     if args.bsa_sparsity is not None:
