@@ -52,7 +52,6 @@ def test_two_rank_nccl_replicas_stay_identical():
     assert out[0] == out[1]
 
 
-@pytest.mark.xfail(strict=False, reason="written without a multi-GPU box at hand; promote once it has run (scratch/next_round_commands.md 7)")
 def test_method_script_under_torchrun(tmp_path):
     """The LoRA script started the way a user would (torchrun, 2 ranks): both ranks finish, rank 0 writes the
     reference's files once, early stopping ran on agreed anchor losses (tests/test_dist_cpu.py covers the host flow on
