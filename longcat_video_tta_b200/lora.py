@@ -196,6 +196,23 @@ def save_lora_weights(lora_modules, path: str):
     torch.save(state, path)
 
 
+def _check_param_list(dit, lora_params):
+    """The fused stepper trains EVERY adapter the engine finds on the DiT, in injection order; the reference's optimizer
+    trains whatever list it is handed (run_lora_tta.py:455-468).  Refuse a list that is not exactly that set instead of
+    silently training (and early-stop snapshotting) different tensors."""
+    eng = getattr(dit, "engine", None)
+    if eng is None:
+        return
+    mine = eng.adapter_parameters()
+    if len(mine) != len(lora_params) or any(a is not b for a, b in zip(mine, lora_params)):
+        raise NotImplementedError(
+            f"the parameter list handed in ({len(lora_params)} tensors) is not the adapter set injected into the DiT "
+            f"({len(mine)} tensors, injection order): training a subset / re-ordered list is not supported by the fused step")
+    flags = [bool(p.requires_grad) for p in lora_params]
+    if any(flags) and not all(flags):
+        raise NotImplementedError("some adapter tensors are frozen and some are not: the fused step trains all of them")
+
+
 def _warmup_lr(lr, step, warmup_steps):
     return lr * (step + 1) / warmup_steps if (warmup_steps > 0 and step < warmup_steps) else lr
 
@@ -210,6 +227,7 @@ def finetune_lora_on_conditioning(dit, lora_modules, cond_latents, train_latents
     lora_params = lora_param_fn() if lora_param_fn is not None else get_lora_parameters(lora_modules)
     if not lora_params:
         raise ValueError("No LoRA parameters found.")
+    _check_param_list(dit, lora_params)
     stepper = TTAStepper(dit, betas=(0.9, 0.999), eps=1e-8, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
                          master_weights=master_weights, faithful_bf16=faithful_bf16, process_group=process_group)
     if train_latents_variants is None:
@@ -256,6 +274,7 @@ def finetune_lora_batch(dit, lora_modules, batch_data: List[Dict], num_steps: in
                         master_weights: bool = True, faithful_bf16: bool = False) -> Dict:
     """run_lora_tta.py:558-634: round-robin over K pre-encoded videos held on the host (one video per step)."""
     lora_params = lora_param_fn() if lora_param_fn is not None else get_lora_parameters(lora_modules)
+    _check_param_list(dit, lora_params)
     stepper = TTAStepper(dit, eps=1e-8, weight_decay=weight_decay, max_grad_norm=max_grad_norm,
                          master_weights=master_weights, faithful_bf16=faithful_bf16)
     dit.train()

@@ -123,7 +123,19 @@ class TTAStepper:
         B, _, Tc, Hl, Wl = cond.shape
         if B != 1:
             raise NotImplementedError("batch size 1 only (every reference run; common.py:448)")
+        if cond.shape[1] != 16 or target.shape[:2] != cond.shape[:2] or target.shape[3:] != cond.shape[3:]:
+            raise ValueError(f"cond {tuple(cond.shape)} / target {tuple(target.shape)}: expected [1,16,T,H,W] with equal H, W")
+        if cond.device != self.eng.device or target.device != self.eng.device:
+            raise ValueError(f"latents must live on {self.eng.device}")
         return Geometry(T=Tc + target.shape[2], Hl=Hl, Wl=Wl, n_cond=Tc, M=text_valid.shape[0])
+
+    @staticmethod
+    def _dense(x: torch.Tensor) -> torch.Tensor:
+        """[16, T, H, W] bf16, densely laid out: the noising kernel reads latents by raw pointer (a frame slice of a
+        longer latent, or randn_like of one, is a strided view -- `.to(bf16)` alone would hand its storage over as is).
+        fp32 latents are rounded to bf16 here, before the (1 - s) x + s eps mix (the reference mixes in fp32 and rounds
+        the result, common.py:463-466: a difference of one bf16 rounding on x0 and eps)."""
+        return x[0].to(BF16).contiguous()
 
     # ------------------------------------------------------------------ CUDA graph of forward + backward
     # The ~6 800 kernel launches of one headline step (140 per block) go through ctypes one by one; with a fixed
@@ -176,7 +188,9 @@ class TTAStepper:
             ex = self.extras = Extras(eng.L)
             ex.need_dmod = ex.need_dt = ex.norm_grads = True
         eng._prepare(geo, ex)
-        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.to(F32))
+        if noise.shape != target.shape:
+            raise ValueError(f"noise {tuple(noise.shape)} must match the target latents {tuple(target.shape)}")
+        eng.set_inputs(self._dense(cond), self._dense(target), self._dense(noise), sigma.to(F32))
         eng.forward_tokens(text_valid, ex, stash=True)
         loss = eng.loss_and_dpred(True)
         only_bias = ex is not None and ex.out_bias is not None and not self._needs_dit_backward()
@@ -236,7 +250,7 @@ class TTAStepper:
         geo = self._geometry(cond, target, text_valid)
         ex = self.adapter.build_extras() if self.adapter is not None else None
         eng._prepare(geo, ex)
-        eng.set_inputs(cond[0].to(BF16), target[0].to(BF16), noise[0].to(BF16), sigma.reshape(-1)[:1].to(F32))
+        eng.set_inputs(self._dense(cond), self._dense(target), self._dense(noise), sigma.reshape(-1)[:1].to(F32))
         eng.forward_tokens(text_valid, ex, ctx=ctx)
         eng._ws_holds = None
         return eng.loss_and_dpred(False).clone()
@@ -250,8 +264,8 @@ class TTAStepper:
         geo = self._geometry(cond, x_t, text_valid)
         ex = self.adapter.build_extras() if self.adapter is not None else None
         eng._prepare(geo, ex)
-        xt = x_t[0].to(BF16)
-        eng.set_inputs(cond[0].to(BF16), xt, xt, sigma.reshape(-1)[:1].to(F32))   # (1 - s) x + s x = x: no re-noising
+        xt = self._dense(x_t)
+        eng.set_inputs(self._dense(cond), xt, xt, sigma.reshape(-1)[:1].to(F32))   # (1 - s) x + s x = x: no re-noising
         eng.forward_tokens(text_valid, ex, ctx=ctx)
         eng._ws_holds = None
         out = torch.empty(16, geo.T, geo.Hl, geo.Wl, dtype=F32, device=eng.device)

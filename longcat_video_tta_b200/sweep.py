@@ -193,7 +193,7 @@ def run_rows(commands: Sequence[Tuple[str, str, List[str]]], gpus: int = 1, pyth
     """Run (run_id, script, argv) rows as local processes; with ``gpus`` > 1 up to that many rows run at a time, row i on
     GPU ``i % gpus`` (``CUDA_VISIBLE_DEVICES``).  Returns [{run_id, returncode}] in row order."""
     done: List[Dict] = [None] * len(commands)     # type: ignore[list-item]
-    running: Dict[int, Tuple[int, subprocess.Popen]] = {}
+    running: Dict[int, Tuple[int, subprocess.Popen, object]] = {}
     nxt = 0
     while nxt < len(commands) or running:
         while nxt < len(commands) and len(running) < max(1, gpus):
@@ -205,17 +205,21 @@ def run_rows(commands: Sequence[Tuple[str, str, List[str]]], gpus: int = 1, pyth
                 done[nxt] = {"run_id": run_id, "returncode": None}
             else:
                 if not (root / script).is_file():
-                    raise NotImplementedError(f"{script} is not part of this build (full-model TTA is out of scope)")
+                    raise NotImplementedError(
+                        f"{script} is not part of this build (for full-model TTA only the functions exist: "
+                        "longcat_video_tta_b200.full.finetune_full_on_conditioning / finetune_full_batch)")
                 env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(gpu)) if gpus > 1 else None
                 log = open(log_dir / f"{run_id}.log", "w") if log_dir else None
                 print(f"  Starting {run_id} on GPU {gpu}: {shlex.join(cmd)}")
-                running[gpu] = (nxt, subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT if log else None))
+                running[gpu] = (nxt, subprocess.Popen(cmd, env=env, stdout=log, stderr=subprocess.STDOUT if log else None), log)
             nxt += 1
-        for gpu, (i, proc) in list(running.items()):
+        for gpu, (i, proc, log) in list(running.items()):
             try:
                 rc = proc.wait(timeout=0.5)
             except subprocess.TimeoutExpired:
                 continue
+            if log is not None:
+                log.close()
             done[i] = {"run_id": commands[i][0], "returncode": rc}
             del running[gpu]
     return done
