@@ -310,18 +310,23 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) qk_norm_rope_fwd_kernel(
     }
     const __nv_bfloat16* xr = X + row * ldx;
     __nv_bfloat16* yr = Y + row * ldy;
-    for (int s = 0; s < n_q + n_k; ++s) {
+    // q heads then k heads as two loops: selecting the weight array through a pointer put both arrays in local memory
+    // (32-byte stack frame, round-2 SASS); four heads in flight hide the load + shuffle-reduction latency of each
+    auto head = [&](int s, const float (&w)[4]) {
         const uint2 u = __ldg(reinterpret_cast<const uint2*>(xr + s * 128 + lane * 4));
         float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
         const float ss = warp_sum(a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y);
         const float rstd = rsqrtf(ss * (1.0f / 128.0f) + eps);
-        const float* w = s < n_q ? wqf : wkf;
         const float y0 = a.x * rstd * w[0], y1 = a.y * rstd * w[1], y2 = b.x * rstd * w[2], y3 = b.y * rstd * w[3];
         uint2 o;
         o.x = pack_bf16x2(y0 * rc.c0 - y1 * rc.s0, y1 * rc.c0 + y0 * rc.s0);
         o.y = pack_bf16x2(y2 * rc.c1 - y3 * rc.s1, y3 * rc.c1 + y2 * rc.s1);
         *reinterpret_cast<uint2*>(yr + s * 128 + lane * 4) = o;
-    }
+    };
+#pragma unroll 4
+    for (int s = 0; s < n_q; ++s) head(s, wqf);
+#pragma unroll 4
+    for (int s = n_q; s < n_q + n_k; ++s) head(s, wkf);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) qk_norm_rope_bwd_kernel(
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) qk_norm_rope_bwd_kernel(
             uint2 b = __ldg(reinterpret_cast<const uint2*>(wk + lane * 4));
             t = unpack_bf16x2(b.x); wkf[0] = t.x; wkf[1] = t.y; t = unpack_bf16x2(b.y); wkf[2] = t.x; wkf[3] = t.y;
         } else { wkf[0] = wkf[1] = wkf[2] = wkf[3] = 0.f; }
-        for (int s = 0; s < n_q + n_k; ++s) {
+        auto head = [&](int s, const float (&w)[4], float (&acc)[4]) {
             const uint2 ux = __ldg(reinterpret_cast<const uint2*>(X + row * ldx + s * 128 + lane * 4));
             const uint2 ug = __ldg(reinterpret_cast<const uint2*>(dY + row * lddy + s * 128 + lane * 4));
             float2 xa = unpack_bf16x2(ux.x), xb = unpack_bf16x2(ux.y);
@@ -354,8 +359,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) qk_norm_rope_bwd_kernel(
             float d[4] = {ga.x * rc.c0 + ga.y * rc.s0, ga.y * rc.c0 - ga.x * rc.s0,
                           gb.x * rc.c1 + gb.y * rc.s1, gb.y * rc.c1 - gb.x * rc.s1};
             const float xh[4] = {xa.x * rstd, xa.y * rstd, xb.x * rstd, xb.y * rstd};
-            const float* w = s < n_q ? wqf : wkf;
-            float* acc = s < n_q ? aq : ak;
             float dot = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { acc[i] += d[i] * xh[i]; d[i] *= w[i]; dot += d[i] * xh[i]; }
@@ -364,7 +367,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) qk_norm_rope_bwd_kernel(
             o.x = pack_bf16x2(rstd * (d[0] - xh[0] * dot), rstd * (d[1] - xh[1] * dot));
             o.y = pack_bf16x2(rstd * (d[2] - xh[2] * dot), rstd * (d[3] - xh[3] * dot));
             *reinterpret_cast<uint2*>(dX + row * lddx + s * 128 + lane * 4) = o;
-        }
+        };
+        // q heads then k heads (compile-time arrays: no local-memory pointer select), four heads in flight
+#pragma unroll 4
+        for (int s = 0; s < n_q; ++s) head(s, wqf, aq);
+#pragma unroll 4
+        for (int s = n_q; s < n_q + n_k; ++s) head(s, wkf, ak);
     }
     if (dwq == nullptr && dwk == nullptr) return;
 #pragma unroll

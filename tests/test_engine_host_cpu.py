@@ -80,3 +80,43 @@ def test_additive_hook_is_folded_and_other_hooks_are_refused(dit):
             HookedModulationAdapter(dit).build_extras()
     finally:
         h.remove()
+
+
+def test_parameter_list_must_be_the_injected_adapter_set():
+    """the fused stepper trains every adapter the engine finds; a subset handed to the loop must be refused."""
+    from longcat_video_tta_b200 import lora
+    d = B200DiT.from_oracle(build_oracle_dit("tiny", seed=0), device="cpu")
+    mods = lora.inject_lora_into_dit(d, rank=4, alpha=8.0, target_modules=["qkv", "proj"])
+    params = lora.get_lora_parameters(mods)
+    lora._check_param_list(d, params)                                   # the full list, in injection order: fine
+    with pytest.raises(NotImplementedError, match="not the adapter set"):
+        lora._check_param_list(d, params[:-2])
+    with pytest.raises(NotImplementedError, match="not the adapter set"):
+        lora._check_param_list(d, list(reversed(params)))
+    params[0].requires_grad_(False)
+    with pytest.raises(NotImplementedError, match="frozen"):
+        lora._check_param_list(d, params)
+
+
+def test_full_model_tta_refuses_partially_frozen_models():
+    from longcat_video_tta_b200 import full
+    d = B200DiT.from_oracle(build_oracle_dit("tiny", seed=0), device="cpu")
+    with pytest.raises(ValueError, match="No trainable parameters"):       # run_full_tta.py:126-128
+        full._check_all_trainable(d)
+    d.blocks[0].attn.qkv.weight.requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="EVERY parameter"):
+        full._check_all_trainable(d)
+    d.requires_grad_(True)
+    assert len(full._check_all_trainable(d)) == sum(1 for _ in d.parameters())
+
+
+def test_full_grads_layout_is_one_flat_buffer_in_parameter_order():
+    from longcat_video_tta_b200.engine import FullGrads
+    d = B200DiT.from_oracle(build_oracle_dit("tiny", seed=0), device="cpu")
+    fg = FullGrads(d)
+    assert fg.flat.dtype == torch.float32 and fg.flat.numel() == sum(p.numel() for p in d.parameters())
+    off = 0
+    for (name, p) in d.named_parameters():
+        g = fg.g(p)
+        assert g.shape == p.shape and g.data_ptr() == fg.flat.data_ptr() + 4 * off and fg.named()[name] is g
+        off += p.numel()
