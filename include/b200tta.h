@@ -313,6 +313,11 @@ int b200tta_mt_adamw(const b200tta_tensor_desc* descs_dev, int32_t n, int64_t ma
 int b200tta_mt_sgd(const b200tta_tensor_desc* descs_dev, int32_t n, int64_t max_numel, const float* coef, float grad_scale,
                    float lr, float weight_decay, b200tta_stream_t stream);
 
+/* dst[i, :] = src[idx[i], :]: bf16 rows of `row_elems` elements (multiple of 8), row strides ldd / lds in elements,
+ * idx int64 [rows].  The block-sparse path's token-order <-> block-major permutations (our layout, see bsa.py). */
+int b200tta_gather_rows(void* dst, int64_t ldd, const void* src, int64_t lds, const int64_t* idx, int64_t rows,
+                        int32_t row_elems, b200tta_stream_t stream);
+
 /* out[c] = sum over rows of A[row, c]  (bf16 in, f32 out; bias gradients of full-model TTA). */
 int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t rows, int32_t C, b200tta_stream_t stream);
 

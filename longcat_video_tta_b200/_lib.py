@@ -80,6 +80,7 @@ SIGNATURES = {
     "b200tta_mt_adamw": [vp, i32, i64, vp, f32, f32, f32, f32, f32, f32, i32, i32, vp],
     "b200tta_mt_sgd": [vp, i32, i64, vp, f32, f32, f32, vp],
     "b200tta_colsum": [vp, vp, i64, i64, i32, vp],
+    "b200tta_gather_rows": [vp, i64, vp, i64, vp, i64, i32, vp],
 }
 
 _lib = None

@@ -73,8 +73,9 @@ def select_blocks(q: torch.Tensor, k: torch.Tensor, sparsity: float = 0.9375, n_
         raise ValueError(f"n_tok={n} must be a multiple of {BLOCK}")
     nb = n // BLOCK
     keep, keep_ctx = row_counts(nb, sparsity, n_context_blocks)
-    qm = q.reshape(nb, BLOCK, H, D).float().mean(1)       # [nb, H, D]
-    km = k.reshape(nb, BLOCK, H, D).float().mean(1)
+    # (mean with dtype=float32 up-casts inside the reduction: no fp32 copy of the 755 MB q / k tensors)
+    qm = q.reshape(nb, BLOCK, H, D).mean(1, dtype=torch.float32)       # [nb, H, D]
+    km = k.reshape(nb, BLOCK, H, D).mean(1, dtype=torch.float32)
     score = torch.einsum("ihd,jhd->hij", qm, km)          # [H, nb, nb]
     eye = torch.eye(nb, dtype=torch.bool, device=q.device)[None]
     score = score.masked_fill(eye, float("inf"))          # the chunk itself is always kept

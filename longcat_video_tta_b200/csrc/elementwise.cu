@@ -408,6 +408,18 @@ __global__ void __launch_bounds__(256) gate_mul_kernel(__nv_bfloat16* __restrict
     }
 }
 
+// dst[i, :] = src[idx[i], :] for rows of `vecs` 16-byte vectors (block-sparse attention: token order <-> block-major order)
+__global__ void __launch_bounds__(256) gather_rows_kernel(uint4* __restrict__ dst, long long ldd_v, const uint4* __restrict__ src,
+                                                          long long lds_v, const long long* __restrict__ idx, long long rows,
+                                                          int vecs) {
+    const long long total = rows * vecs;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / vecs;
+        const int c = (int)(i - r * vecs);
+        dst[r * ldd_v + c] = __ldg(src + __ldg(idx + r) * lds_v + c);
+    }
+}
+
 // acc[f, c] += sum over rows of frame f of A[row, c] * B[row, c]  (B == nullptr -> sum of A)
 __global__ void __launch_bounds__(256) colsum_prod_kernel(float* __restrict__ acc, long long acc_ld,
                                                           const __nv_bfloat16* __restrict__ A, long long lda,
@@ -795,6 +807,18 @@ extern "C" int b200tta_gate_mul(void* dY, int64_t lddy, const void* dX, int64_t 
                                               (const __nv_bfloat16*)branch, ldb, rows, C, tokens_per_frame, rpb);
         B200_LAUNCHED();
     }
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_gather_rows(void* dst, int64_t ldd, const void* src, int64_t lds, const int64_t* idx, int64_t rows,
+                                   int32_t row_elems, b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(dst && src && idx && rows > 0 && row_elems > 0 && row_elems % 8 == 0 && ldd % 8 == 0 && lds % 8 == 0 &&
+                     aligned16(dst) && aligned16(src),
+                 "gather_rows: bf16 rows must be 16-byte aligned with a length that is a multiple of 8");
+    gather_rows_kernel<<<grid_for(rows * (row_elems / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (uint4*)dst, ldd / 8, (const uint4*)src, lds / 8, (const long long*)idx, rows, row_elems / 8);
+    B200_LAUNCHED();
     return B200TTA_OK;
 }
 

@@ -685,9 +685,9 @@ class TTAEngine:
     def _bsa_gather(self, q, k, v):
         ws, N, H, D = self.ws, self.geo.N, self.H, self.D
         bq, bk, bv = (t.view(N, H, D) for t in (ws.bq, ws.bk, ws.bv))
-        torch.index_select(q, 0, ws.bsa_perm, out=bq)     # (t, h, w) row-major -> block-major token order
-        torch.index_select(k, 0, ws.bsa_perm, out=bk)
-        torch.index_select(v, 0, ws.bsa_perm, out=bv)
+        ops.gather_rows(bq, q, ws.bsa_perm)               # (t, h, w) row-major -> block-major token order
+        ops.gather_rows(bk, k, ws.bsa_perm)
+        ops.gather_rows(bv, v, ws.bsa_perm)
         return bq, bk, bv
 
     def _bsa_fwd(self, b: int, q, k, v):
@@ -699,21 +699,21 @@ class TTAEngine:
         lists = _bsa.select_blocks(bq, bk, self.bsa["sparsity"], ws.bsa_nctx)
         ws.bsa_lists[b] = lists
         ops.attn_bsa_fwd(bq, bk, bv, ws.bo.view(N, H, D), ws.lse, lists.q_off, lists.q_idx, self.softmax_scale)
-        torch.index_select(ws.bo.view(N, H, D), 0, ws.bsa_inv, out=ws.o.view(N, H, D))
+        ops.gather_rows(ws.o.view(N, H, D), ws.bo.view(N, H, D), ws.bsa_inv)
 
     def _bsa_bwd(self, b: int, dq, dk, dv, do, q, k, v):
         ws, N, H, D = self.ws, self.geo.N, self.H, self.D
         lists = ws.bsa_lists[b]
         bq, bk, bv = self._bsa_gather(q, k, v)
         bo, bdo = ws.bo.view(N, H, D), ws.bdo.view(N, H, D)
-        torch.index_select(ws.o.view(N, H, D), 0, ws.bsa_perm, out=bo)
-        torch.index_select(do, 0, ws.bsa_perm, out=bdo)
+        ops.gather_rows(bo, ws.o.view(N, H, D), ws.bsa_perm)
+        ops.gather_rows(bdo, do, ws.bsa_perm)
         bdq, bdk, bdv = (t.view(N, H, D) for t in (ws.bdq, ws.bdk, ws.bdv))
         ops.attn_bsa_bwd(bdq, bdk, bdv, bdo, bo, ws.lse, ws.delta, bq, bk, bv, lists.q_off, lists.q_idx, lists.k_off,
                          lists.k_idx, self.softmax_scale)
-        dq.copy_(bdq.index_select(0, ws.bsa_inv))
-        dk.copy_(bdk.index_select(0, ws.bsa_inv))
-        dv.copy_(bdv.index_select(0, ws.bsa_inv))
+        ops.gather_rows(dq, bdq, ws.bsa_inv)              # straight into the strided dq / dk / dv views
+        ops.gather_rows(dk, bdk, ws.bsa_inv)
+        ops.gather_rows(dv, bdv, ws.bsa_inv)
 
     # ------------------------------------------------------------------ forward with cached context K/V
     # The context (clean conditioning) frames carry timestep 0 and only attend to themselves, so for a fixed video, text

@@ -281,6 +281,15 @@ def lora_grad(G, P, Q):
     _call("b200tta_lora_grad", _p(G), _p(P), _ld(P), _p(Q), _ld(Q), n_tok, m, r, _stream())
 
 
+def gather_rows(dst, src, idx):
+    """dst[i] = src[idx[i]] for [rows, ...] bf16 tensors whose trailing dims are dense (row stride arbitrary); idx int64"""
+    rows = dst.shape[0]
+    row_elems = dst[0].numel()
+    _req(dst, BF16, "gather_rows dst")
+    _req(src, BF16, "gather_rows src")
+    _call("b200tta_gather_rows", _p(dst), dst.stride(0), _p(src), src.stride(0), _p(idx), rows, row_elems, _stream())
+
+
 def colsum(out, a):
     """out [C] f32 = column sums of a [rows, C] bf16 (row stride arbitrary)"""
     rows, Cdim = a.shape
