@@ -56,3 +56,38 @@ def test_kernel_table_reports_tensor_pipe_fractions():
     assert t["ln_mod_fwd"] == {"ms": 46.8, "n": 265, "tflops": None}
     import json
     json.dumps(t)
+
+
+def test_reference_arm_line_says_what_was_timed_and_what_is_extrapolated(monkeypatch, capsys):
+    """ADVICE r1 / VERDICT r1 weak 9: the CPU arm must not pass an extrapolation off as a measurement.  With the block
+    sample stubbed (1 + 1 frames take 2 s, 4 + k frames take 2 s per frame) the line must carry the seconds and steps really
+    timed, the scale factor, `extrapolated: true`, kind `port-extrapolated`, and configs[0] measured whole inside it."""
+    import json
+    import types
+    import bench
+    calls = []
+
+    def fake_block(Tc, Tt, threads, steps=1):
+        calls.append((Tc, Tt, steps))
+        return 2.0 if (Tc, Tt) == (1, 1) else 2.0 * (Tc + Tt)
+
+    monkeypatch.setattr(bench, "_cpu_block_sample", fake_block)
+    monkeypatch.setattr(bench, "cpu_tiny_sample", lambda threads, **kw: {"value": 10.0, "unit": bench.UNIT, "cores": threads,
+                                                                         "kind": "port", "sample": "configs[0] stub"})
+    monkeypatch.setattr(bench, "_mem_available_bytes", lambda: 200e9)
+    out = []
+    monkeypatch.setattr(bench, "_OUT", types.SimpleNamespace(write=out.append, flush=lambda: None))
+    monkeypatch.delenv("RANK", raising=False)
+    bench.run_reference(types.SimpleNamespace(gpus=1, ref_budget_s=1e9))
+    line = json.loads("".join(out))
+    assert calls == [(1, 1, 2), (4, 20, 1)]                      # probe (second step timed), then the full 24 frames
+    assert line["impl"] == "reference" and line["extrapolated"] is True and line["scale_factor"] == 48.0
+    assert line["timed"]["sample_seconds"] == 48.0 and line["timed"]["sample_tokens"] == 37440 and line["steps"] == 1
+    assert line["value"] == pytest.approx(1.0 / (48.0 * 48.0)) and line["e2e"]["value"] == line["value"]
+    assert line["cpu_baseline"]["kind"] == "port-extrapolated" and line["cpu_baseline"]["config0"]["value"] == 10.0
+    # a tight budget falls back to fewer frames and says so through the FLOP ratio
+    calls.clear(); out.clear()
+    bench.run_reference(types.SimpleNamespace(gpus=1, ref_budget_s=30.0))
+    line = json.loads("".join(out))
+    assert calls[0] == (1, 1, 2) and calls[1][0] == 4 and calls[1][1] < 20
+    assert line["scale_factor"] > 48.0 and "algorithmic-FLOP ratio" in line["cpu_baseline"]["sample"]
