@@ -420,6 +420,25 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(uint4* __restrict__ ds
     }
 }
 
+// out[c] += sum over a slab of rows of A[row, c]: 8 columns per thread (one 128-bit load per row), fp32 atomics per slab
+__global__ void __launch_bounds__(256) colsum8_kernel(float* __restrict__ out, const __nv_bfloat16* __restrict__ A, long long lda,
+                                                      long long rows, int C, int rows_per_block) {
+    const int col = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (col >= C) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(A + r * lda + col)), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(out + col + i, s[i]);
+}
+
 // acc[f, c] += sum over rows of frame f of A[row, c] * B[row, c]  (B == nullptr -> sum of A)
 __global__ void __launch_bounds__(256) colsum_prod_kernel(float* __restrict__ acc, long long acc_ld,
                                                           const __nv_bfloat16* __restrict__ A, long long lda,
@@ -827,9 +846,19 @@ extern "C" int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t ro
     B200_REQUIRE(out && A && rows > 0 && C > 0, "colsum: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     B200_CUDA(cudaMemsetAsync(out, 0, (size_t)C * sizeof(float), st));
-    const int rpb = 256;
-    dim3 g((C + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
-    colsum_prod_kernel<<<g, 256, 0, st>>>(out, 0, (const __nv_bfloat16*)A, lda, nullptr, 0, rows, C, (int)(rows > 2147483647ll ? 2147483647ll : rows), rpb);
+    if (C % 8 == 0 && lda % 8 == 0 && aligned16(A)) {
+        // enough row slabs to fill the chip whatever the width: ~8 blocks per SM
+        const int xb = (C / 8 + 255) / 256;
+        int rpb = (int)((rows * xb + 148 * 8 - 1) / (148 * 8));
+        rpb = rpb < 32 ? 32 : rpb;
+        dim3 g((unsigned)xb, (unsigned)((rows + rpb - 1) / rpb));
+        colsum8_kernel<<<g, 256, 0, st>>>(out, (const __nv_bfloat16*)A, lda, rows, C, rpb);
+    } else {
+        const int rpb = 256;
+        dim3 g((C + 255) / 256, (unsigned)((rows + rpb - 1) / rpb));
+        colsum_prod_kernel<<<g, 256, 0, st>>>(out, 0, (const __nv_bfloat16*)A, lda, nullptr, 0, rows, C,
+                                              (int)(rows > 2147483647ll ? 2147483647ll : rows), rpb);
+    }
     B200_LAUNCHED();
     return B200TTA_OK;
 }

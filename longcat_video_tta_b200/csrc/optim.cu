@@ -27,9 +27,19 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_kernel(const b200tta_tensor
     __shared__ float red[OPT_THREADS / 32];
     const b200tta_tensor_desc d = descs[blockIdx.y];
     float s = 0.f;
-    for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < d.numel; i += (long long)gridDim.x * OPT_THREADS) {
-        const float g = d.grad[i];  // layout does not matter for a sum of squares
-        s += g * g;
+    if ((d.numel & 3) == 0 && (reinterpret_cast<uintptr_t>(d.grad) & 15) == 0) {
+        const float4* G4 = reinterpret_cast<const float4*>(d.grad);
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < (d.numel >> 2); i += (long long)gridDim.x * OPT_THREADS) {
+            const float4 g = G4[i];
+            s4[0] = fmaf(g.x, g.x, s4[0]); s4[1] = fmaf(g.y, g.y, s4[1]); s4[2] = fmaf(g.z, g.z, s4[2]); s4[3] = fmaf(g.w, g.w, s4[3]);
+        }
+        s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    } else {
+        for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < d.numel; i += (long long)gridDim.x * OPT_THREADS) {
+            const float g = d.grad[i];  // layout does not matter for a sum of squares
+            s += g * g;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -128,6 +138,28 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_kernel(const b200tta_tensor_d
                                                           const float* __restrict__ coef, float grad_scale, float lr, float wd) {
     const b200tta_tensor_desc d = descs[blockIdx.y];
     const float c = (coef ? coef[blockIdx.y] : 1.0f) * grad_scale;
+    // the 13.6 B-parameter case: bf16 parameter without master, plain gradient layout -> 8 elements per thread, 128-bit accesses
+    if (d.is_bf16 && d.master == nullptr && d.t_rows == 0 && (d.numel & 7) == 0 &&
+        ((reinterpret_cast<uintptr_t>(d.param) | reinterpret_cast<uintptr_t>(d.grad)) & 15) == 0) {
+        uint4* P8 = reinterpret_cast<uint4*>(d.param);
+        const float4* G4 = reinterpret_cast<const float4*>(d.grad);
+        const long long n8 = d.numel >> 3;
+        for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < n8; i += (long long)gridDim.x * OPT_THREADS) {
+            uint4 u = P8[i];
+            const float4 g0 = G4[2 * i], g1 = G4[2 * i + 1];
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 pv = unpack_bf16x2(w[k]);
+                pv.x -= lr * (g[2 * k] * c + wd * pv.x);
+                pv.y -= lr * (g[2 * k + 1] * c + wd * pv.y);
+                w[k] = pack_bf16x2(pv.x, pv.y);
+            }
+            P8[i] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        return;
+    }
     for (long long i = (long long)blockIdx.x * OPT_THREADS + threadIdx.x; i < d.numel; i += (long long)gridDim.x * OPT_THREADS) {
         float p = d.master ? d.master[i]
                            : (d.is_bf16 ? __bfloat162float(reinterpret_cast<__nv_bfloat16*>(d.param)[i])

@@ -549,3 +549,35 @@ def test_gemm_headline_size_slices(ops):
     dx = torch.empty(M, K, dtype=BF16, device="cuda")
     ops.gemm(M, K, [(out, w, N, True, None)], ops.epi(ops.EPI_STORE, dx))
     close(dx[rows], out[rows].float() @ w.float())
+
+
+# ---------------------------------------------------------------------------------------------- full-model TTA helpers
+@pytest.mark.parametrize("rows,C", [(1000, 64), (3120, 4096), (513, 12288), (37, 40)])
+def test_colsum(ops, rows, C):
+    big = rnd(rows, C + 8, seed=31)
+    a = big[:, 8:] if C % 8 == 0 else big[:, :C].contiguous()          # strided view (a slice of a fused buffer)
+    out = torch.full((C,), float("nan"), dtype=F32, device="cuda")
+    ops.colsum(out, a)
+    close(out, a.float().sum(0), rtol=1e-3, atol=1e-2 * (rows ** 0.5))
+
+
+def test_mt_sgd_matches_torch_sgd(ops):
+    """b200tta_mt_sgd == torch.optim.SGD(momentum=0, weight_decay) on bf16 parameters with fp32 gradients: the vectorised
+    path (numel % 8 == 0), the scalar path, an fp32 parameter, a clip coefficient and a gradient scale."""
+    shapes = [(64, 128), (7, 9), (4096,)]
+    g = torch.Generator(device="cuda").manual_seed(7)
+    params = [torch.randn(s, generator=g, device="cuda").to(BF16 if i < 2 else F32) for i, s in enumerate(shapes)]
+    grads = [torch.randn(s, generator=g, device="cuda") for s in shapes]
+    ref = [p.clone().float() for p in params]
+    entries = [dict(param=p, grad=gr) for p, gr in zip(params, grads)]
+    tl = ops.TensorList(entries, torch.device("cuda"))
+    lr, wd, gs = 0.5, 0.01, 0.25
+    tl.clip_coef(1.0, grad_scale=gs)
+    total = torch.sqrt(sum((gr.float() ** 2).sum() for gr in grads)) * gs
+    coef = min(1.0, 1.0 / (total.item() + 1e-6))
+    tl.sgd(lr=lr, weight_decay=wd, grad_scale=gs)
+    for p, r, gr in zip(params, ref, grads):
+        want = r - lr * (gr * gs * coef + wd * r)
+        if p.dtype == BF16:
+            want = want.to(BF16)
+        assert torch.equal(p, want.to(p.dtype)) or (p.float() - want.float()).abs().max() <= 2 ** -8 * want.float().abs().max()
