@@ -396,7 +396,10 @@ class TTAEngine:
         ws.tfeat, ws.th, ws.t = e(T, self.dit.config.frequency_embedding_size, dt=F32), e(T, self.Ct, dt=F32), e(T, self.Ct, dt=F32)
         ws.t_blk = e(T, self.Ct, dt=F32)
         ws.y1, ws.y = e(M, C), e(M, C)
-        ws.mod, ws.modf = e(T, 6 * C, dt=F32), e(T, 2 * C, dt=F32)
+        # adaLN modulation of every block (2.4 MB each at T = 24): the recompute pass re-uses it instead of re-running
+        # the [T, 512] x [6C, 512]^T product (a 135 us latency-bound launch per block)
+        ws.mod_all, ws.modf = e(self.L, T, 6 * C, dt=F32), e(T, 2 * C, dt=F32)
+        ws.mod = ws.mod_all[0]
         ws.xm1, ws.xm2 = e(N, C), e(N, C)
         ws.qkv_tmp, ws.qk = e(N, 3 * C), e(N, 2 * C)
         # self-attention output + log-sum-exp are kept for EVERY block (312 MB per block at 37k tokens) so that the
@@ -468,6 +471,7 @@ class TTAEngine:
         """Point the per-block workspace names at block b's slots."""
         ws, st = self.ws, self._stash if self._stash_on else None
         ws.o, ws.lse = ws.o_all[b], ws.lse_all[b]
+        ws.mod = ws.mod_all[b]
         ws.x1 = st["x1"][b, 0] if st and b < st["k_x1"] else ws.x1_tmp
         ws.x2 = st["x2"][b, 0] if st and b < st["k_x2"] else ws.x2_tmp
         ws.qkv = st["qkv"][b, 0] if st and b < st["k_qkv"] else ws.qkv_tmp
@@ -594,7 +598,8 @@ class TTAEngine:
             raise NotImplementedError(
                 "forward hooks on blocks[%d].adaLN_modulation are only honoured through B200DiT.forward(); for the fused "
                 "stepper use longcat_video_tta_b200.adapters.FiLMAdapterWrapper (same constructor as the reference's)" % b)
-        ops.skinny_linear(ws.mod, self._t_for_block(b, ex), ada.weight, ada.bias, act=1, addend=film)
+        if not recompute:      # the recompute pass finds this block's modulation where the forward left it
+            ops.skinny_linear(ws.mod, self._t_for_block(b, ex), ada.weight, ada.bias, act=1, addend=film)
         mod = ws.mod
         shift_msa, scale_msa, gate_msa = mod[:, 0:C], mod[:, C:2 * C], mod[:, 2 * C:3 * C]
         shift_mlp, scale_mlp, gate_mlp = mod[:, 3 * C:4 * C], mod[:, 4 * C:5 * C], mod[:, 5 * C:6 * C]
