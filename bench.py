@@ -510,6 +510,9 @@ def run_b200(args):
         roof = {"kernel": fam, "bound": "tensor", "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tflops_sustained"], "traffic": _ncu_traffic(fam),
                 "peak_source": peaks["source"] + " cuBLAS bf16, sustained figure (kernel timed inside a long step)",
+                "kernels": ("delta_kernel + dkvq_kernel (five products, fused) + dq_convert_kernel"
+                            if os.environ.get("B200TTA_ATTN_BWD", "fused") != "split" else "delta_kernel + dq_kernel + dkv_kernel")
+                if fam == "attn_bwd[self]" else fam,
                 "launches_per_step": d["n"], "avg_launch_ms": d["ms"] / d["n"],
                 "algorithmic_tflop_per_launch": d["flops"] / d["n"] / 1e12, "share_of_step": d["ms"] / tot_ms}
     cpu = cpu_tiny = None
@@ -604,7 +607,7 @@ def _call_flops(name, a):
     if name in ("b200tta_attn_bsa_fwd", "b200tta_attn_bsa_bwd"):   # 128 x 128 token pairs actually attended (set by main)
         heads = a[10] if name.endswith("fwd") else a[19]
         return 4.0 * heads * 128 * _BSA["pairs_per_head"] * (1.0 if name.endswith("fwd") else 2.5)
-    if name in ("b200tta_attn_fwd", "b200tta_attn_bwd"):
+    if name in ("b200tta_attn_fwd", "b200tta_attn_bwd", "b200tta_attn_bwd_fused"):   # the fused entry shares attn_bwd's leading arguments
         segs, n_seg, heads = (a[13], a[14], a[11]) if name.endswith("fwd") else (a[22], a[23], a[20])
         pairs = sum((segs[i].q_end - segs[i].q_begin) * segs[i].kv_len for i in range(n_seg))
         return 4.0 * heads * 128 * pairs * (1.0 if name.endswith("fwd") else 2.5)
@@ -616,6 +619,8 @@ _BSA = {"pairs_per_head": 0.0}
 
 def _family(name, a):
     fam = name.replace("b200tta_", "")
+    if fam == "attn_bwd_fused":     # same operation, same family: which kernels ran is recorded in roofline.kernels
+        fam = "attn_bwd"
     if fam in ("attn_bsa_fwd", "attn_bsa_bwd"):
         return fam.replace("_bsa", "") + "[self, block-sparse]"
     if fam in ("attn_fwd", "attn_bwd"):
@@ -630,10 +635,13 @@ def _family(name, a):
 
 def _ncu_traffic(family):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel family from the
-    committed `ncu --set full` capture (profiles/r1_ncu_attention_full.json, headline shape); None if not captured.
-    attn_bwd[self] = dq_kernel + dkv_kernel (the delta pre-pass, 0.6 GB algorithmic, was not captured)."""
-    kernels = {"attn_bwd[self]": ("dq_kernel", "dkv_kernel"), "attn_fwd[self]": ("attn_fwd",)}.get(family)
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_attention_full.json")
+    committed `ncu --set full` captures (profiles/r2_ncu_kernels_full.json, headline shape, one launch per kernel); None if
+    not captured.  attn_bwd[self] = dkvq_kernel (fused, the default) or dq_kernel + dkv_kernel (B200TTA_ATTN_BWD=split);
+    the delta pre-pass and the fp32 -> bf16 dQ conversion (0.6 + 0.9 GB algorithmic) were not captured."""
+    fused = os.environ.get("B200TTA_ATTN_BWD", "fused") != "split"
+    kernels = {"attn_bwd[self]": ("dkvq_kernel",) if fused else ("dq_kernel", "dkv_kernel"),
+               "attn_fwd[self]": ("attn_fwd_kernel",)}.get(family)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ncu_kernels_full.json")
     if kernels is None or not os.path.exists(path):
         return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -144,14 +144,16 @@ def _dq_accumulator(n_q: int, width: int, device) -> torch.Tensor:
 
 
 def attn_bwd(dq, dk, dv, do, o, lse, delta, q, k, v, segs, softmax_scale: float, fused: Optional[bool] = None):
-    """split (default): dq_kernel + dkv_kernel (seven products per tile pair, no atomics, no workspace);
-    fused (B200TTA_ATTN_BWD=fused or fused=True): ONE kernel forms dK, dV and the dQ partial products (five products per
-    tile pair, dQ through asynchronous fp32 TMA reduce-adds into a [heads, n_q, 128] workspace).  Both are parity-tested;
-    measured at the headline shape they tie (52.3 vs 53.5 ms stand-alone, 5.36 vs 5.40 s per step): the fused kernel is
-    bound by shared-memory bandwidth instead of tensor issue."""
+    """fused (default): ONE kernel forms dK, dV and the dQ partial products (five products per tile pair, dQ through
+    asynchronous fp32 TMA reduce-adds into a [heads, n_q, 128] workspace kept per device);
+    split (B200TTA_ATTN_BWD=split or fused=False): dq_kernel + dkv_kernel (seven products per tile pair, no atomics, no
+    workspace).  Both are parity-tested at every size.  Stand-alone they tie (52.3 vs 53.5 ms at the headline shape, both
+    bound by shared-memory bandwidth); inside the power-capped step the fused kernel's two fewer tensor-core
+    products per tile pair buy clock for everything else: 5.32-5.33 s vs 5.37-5.38 s per step, alternating on one box
+    (profiles/r2_bench_attn_bwd_split_vs_fused.json)."""
     n_q, H, D = q.shape
     if fused is None:
-        fused = os.environ.get("B200TTA_ATTN_BWD", "split") == "fused"
+        fused = os.environ.get("B200TTA_ATTN_BWD", "fused") != "split"
     if fused:
         acc = _dq_accumulator(n_q, H * D, q.device)
         _call("b200tta_attn_bwd_fused", _p(dq), dq.stride(0), _p(dk), dk.stride(0), _p(dv), dv.stride(0), _p(do), do.stride(0),

@@ -581,3 +581,34 @@ def test_mt_sgd_matches_torch_sgd(ops):
         if p.dtype == BF16:
             want = want.to(BF16)
         assert torch.equal(p, want.to(p.dtype)) or (p.float() - want.float()).abs().max() <= 2 ** -8 * want.float().abs().max()
+
+
+def test_gather_rows_roundtrip_at_720p_size(ops):
+    """block-sparse path: token order -> block-major -> token order is the identity (92 160 tokens x 4096, strided views)"""
+    from longcat_video_tta_b200 import bsa
+    n, H, D = 92160, 32, 128
+    perm, inv = bsa.block_permutation(24, 48, 80, (4, 4, 8), device="cuda")
+    qk = rnd(n, 2 * H * D, seed=41).view(n, 2 * H, D)
+    q = qk[:, :H]                                            # row stride 2 C, as in the engine
+    b = torch.empty(n, H, D, dtype=BF16, device="cuda")
+    ops.gather_rows(b, q, perm)
+    assert torch.equal(b, q.index_select(0, perm))
+    back = torch.full_like(qk, float("nan"))
+    ops.gather_rows(back[:, :H], b, inv)
+    assert torch.equal(back[:, :H], q)
+    assert torch.isnan(back[:, H:].float()).all()            # nothing written outside the destination view
+
+
+def test_weight_gradient_gemm_headline_size_slices(ops):
+    """dW of the qkv projection at the headline token count: [12288, 4096] = dY[37440, 12288]^T X[37440, 4096], fp32 out,
+    checked on random rows against fp32 and through linearity (dW(2 dY) = 2 dW(dY) exactly: x2 is exact in bf16)."""
+    K, M, N = HEAD_N, 3 * 4096, 4096
+    dy, x = rnd(K, M, scale=0.05, seed=51), rnd(K, N, scale=0.5, seed=52)
+    dw = torch.empty(M, N, dtype=F32, device="cuda")
+    ops.gemm(M, N, [(dy, x, K, True, None, True)], ops.epi(ops.EPI_STORE_F32, dw))
+    rows = torch.randint(0, M, (96,), device="cuda", generator=torch.Generator(device="cuda").manual_seed(2))
+    ref = dy[:, rows].float().t() @ x.float()
+    close(dw[rows], ref)
+    dw2 = torch.empty_like(dw)
+    ops.gemm(M, N, [((dy.float() * 2).to(BF16), x, K, True, None, True)], ops.epi(ops.EPI_STORE_F32, dw2))
+    assert ((dw2 - 2 * dw).norm() / (2 * dw).norm()).item() < 1e-5
