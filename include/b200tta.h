@@ -70,7 +70,9 @@ enum {
                                    d2 (optional) = bf16(acc + bias) */
     B200TTA_EPI_SWIGLU = 4,     /* N tile = [h1 | h3]: d[:, n/2] = bf16(silu(h1) * h3); d2, d3 (optional) = h1, h3 */
     B200TTA_EPI_SWIGLU_BWD = 5, /* acc = dh: d = bf16(dh * h3 * silu'(h1)), d2 = bf16(dh * silu(h1)); aux1 = h1, aux2 = h3 */
-    B200TTA_EPI_MUL_GATE_IN = 6 /* d = bf16(acc + bias) (reserved) */
+    B200TTA_EPI_MUL_GATE_IN = 6, /* d = bf16(acc + bias) (reserved) */
+    B200TTA_EPI_GEGLU = 7       /* SWIGLU's tile layout with d = bf16(gelu_tanh(h1) * h3): the UMT5 feed-forward
+                                   (gated-gelu: wi_0, wi_1; text encoder of common.py:228-255) */
 };
 
 typedef struct {

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-            if (p.epi.mode == B200TTA_EPI_SWIGLU) {
+            if (p.epi.mode == B200TTA_EPI_SWIGLU || p.epi.mode == B200TTA_EPI_GEGLU) {
                 // accumulator columns [0, BN/2) = h1, [BN/2, BN) = h3 of output features n0/2 ...
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
@@ -348,8 +348,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_kernel(const __grid_const
                             store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d2) + row * p.epi.ldd2 + col, h1);
                         if (p.epi.d3 != nullptr)
                             store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d3) + row * p.epi.ldd3 + col, h3);
+                        if (p.epi.mode == B200TTA_EPI_GEGLU) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) h1[i] = h1[i] / (1.0f + __expf(-h1[i])) * h3[i];
+                            for (int i = 0; i < 32; ++i) h1[i] = gelu_tanh(h1[i]) * h3[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) h1[i] = h1[i] / (1.0f + __expf(-h1[i])) * h3[i];
+                        }
                         store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d) + row * p.epi.ldd + col, h1);
                     }
                 }
@@ -538,7 +543,7 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm2_kernel(const __grid_con
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-            if (p.epi.mode == B200TTA_EPI_SWIGLU) {
+            if (p.epi.mode == B200TTA_EPI_SWIGLU || p.epi.mode == B200TTA_EPI_GEGLU) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     uint32_t r1[32], r3[32];
@@ -556,8 +561,13 @@ __global__ void __launch_bounds__(NUM_THREADS2, 1) gemm2_kernel(const __grid_con
                             store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d2) + row * p.epi.ldd2 + col, h1);
                         if (p.epi.d3 != nullptr)
                             store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d3) + row * p.epi.ldd3 + col, h3);
+                        if (p.epi.mode == B200TTA_EPI_GEGLU) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) h1[i] = h1[i] / (1.0f + __expf(-h1[i])) * h3[i];
+                            for (int i = 0; i < 32; ++i) h1[i] = gelu_tanh(h1[i]) * h3[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) h1[i] = h1[i] / (1.0f + __expf(-h1[i])) * h3[i];
+                        }
                         store_bf16x32(reinterpret_cast<__nv_bfloat16*>(p.epi.d) + row * p.epi.ldd + col, h1);
                     }
                 }
@@ -643,11 +653,11 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
     B200_REQUIRE(M > 0 && N > 0 && M < (1ll << 31) && N < (1ll << 31), "gemm: bad M=%lld N=%lld", (long long)M, (long long)N);
     B200_REQUIRE(nseg >= 1 && nseg <= MAX_SEG, "gemm: nseg=%d not in [1,%d]", nseg, MAX_SEG);
     B200_REQUIRE(segs && epi && epi->d, "gemm: null segs/epi/output");
-    const bool swiglu = epi->mode == B200TTA_EPI_SWIGLU;
+    const bool swiglu = epi->mode == B200TTA_EPI_SWIGLU || epi->mode == B200TTA_EPI_GEGLU;
     B200_REQUIRE(N % 64 == 0, "gemm: N=%lld must be a multiple of 64", (long long)N);
     const int BN = (N % 256 == 0 || N > 256) ? 256 : 64;
     B200_REQUIRE(BN == 64 || N % 32 == 0, "gemm: N tail");
-    B200_REQUIRE(!swiglu || (N % 256 == 0), "gemm: SWIGLU needs N (=2F) %% 256 == 0");
+    B200_REQUIRE(!swiglu || (N % 256 == 0), "gemm: SWIGLU / GEGLU need N (=2F) %% 256 == 0");
 
     GemmParams p;
     memset(&p, 0, sizeof(p));
