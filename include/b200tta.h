@@ -323,6 +323,24 @@ int b200tta_gather_rows(void* dst, int64_t ldd, const void* src, int64_t lds, co
 /* out[c] = sum over rows of A[row, c]  (bf16 in, f32 out; bias gradients of full-model TTA). */
 int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t rows, int32_t C, b200tta_stream_t stream);
 
+/* ---- text encoder (text half): encode_prompt, delta_experiment/scripts/common.py:228-255, which calls
+ * transformers' UMT5EncoderModel.  Linear layers go through b200tta_gemm (B200TTA_EPI_GEGLU for wi_0 | wi_1,
+ * B200TTA_EPI_GATE_RESID with gate NULL for the residual adds), the embedding lookup through b200tta_gather_rows. */
+
+/* UMT5LayerNorm: Y = bf16(w * bf16(X * rsqrt(mean(X^2) + eps))), no mean subtraction, no bias.  X, Y bf16 [rows, C]
+ * (row strides ldx / ldy elements), w bf16 [C]; C a multiple of 8, at most 4096. */
+int b200tta_t5_rmsnorm(void* Y, int64_t ldy, const void* X, int64_t ldx, const void* w, int64_t rows, int32_t C, float eps,
+                       b200tta_stream_t stream);
+
+/* UMT5Attention core: O = softmax(Q K^T + rel_bias[head, key - query] + key mask) V per (batch item, head); head_dim 64,
+ * NO 1/sqrt(d) scaling.  Q/K/V/O bf16 [batch * n_tok, heads * 64] views (row strides in elements);
+ * rel_bias f32 [heads, 2 * n_tok - 1] indexed by (key - query) + n_tok - 1 (the bucketed table of the layer expanded per
+ * distance); key_valid int32 [batch, n_tok] (0 = padded key, gets finfo(float32).min like transformers' extended mask)
+ * or NULL. */
+int b200tta_t5_attn(void* O, int64_t ldo, const void* Q, int64_t ldq, const void* K, int64_t ldk, const void* V,
+                    int64_t ldv, const float* rel_bias, const int32_t* key_valid, int32_t n_tok, int32_t heads,
+                    int32_t batch, b200tta_stream_t stream);
+
 
 #ifdef __cplusplus
 }

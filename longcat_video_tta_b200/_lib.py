@@ -40,6 +40,7 @@ class TensorDesc(C.Structure):
 
 
 EPI_STORE, EPI_STORE_F32, EPI_GELU, EPI_GATE_RESID, EPI_SWIGLU, EPI_SWIGLU_BWD = 0, 1, 2, 3, 4, 5
+EPI_GEGLU = 7
 
 # name -> argtypes (restype is int32 unless noted); mirrors include/b200tta.h one to one
 SIGNATURES = {
@@ -81,6 +82,8 @@ SIGNATURES = {
     "b200tta_mt_sgd": [vp, i32, i64, vp, f32, f32, f32, vp],
     "b200tta_colsum": [vp, vp, i64, i64, i32, vp],
     "b200tta_gather_rows": [vp, i64, vp, i64, vp, i64, i32, vp],
+    "b200tta_t5_rmsnorm": [vp, i64, vp, i64, vp, i64, i32, f32, vp],
+    "b200tta_t5_attn": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp],
 }
 
 _lib = None

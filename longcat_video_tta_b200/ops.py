@@ -12,7 +12,7 @@ import torch
 
 from . import _lib
 from ._lib import (AttnSeg, GemmEpi, GemmSeg, TensorDesc, EPI_GATE_RESID, EPI_GELU, EPI_STORE, EPI_STORE_F32,
-                   EPI_SWIGLU, EPI_SWIGLU_BWD, check)
+                   EPI_SWIGLU, EPI_SWIGLU_BWD, EPI_GEGLU, check)
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -341,3 +341,28 @@ class TensorList:
         _call("b200tta_mt_adamw", _p(self.dev), self.n, self.max_numel, _p(self.coef) if use_coef else None,
               float(grad_scale), float(lr), float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
               int(faithful_bf16), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ text encoder
+def t5_rmsnorm(y, x, w, eps: float):
+    """UMT5LayerNorm on bf16 rows: y = bf16(w * bf16(x * rsqrt(mean(x^2) + eps)))"""
+    _req(y, BF16, "t5_rmsnorm y")
+    _req(x, BF16, "t5_rmsnorm x")
+    _req(w, BF16, "t5_rmsnorm w")
+    rows, Cdim = x.shape
+    _call("b200tta_t5_rmsnorm", _p(y), _ld(y), _p(x), _ld(x), _p(w), rows, Cdim, float(eps), _stream())
+
+
+def t5_attn(o, q, k, v, rel_bias, key_valid, n_tok: int, heads: int, batch: int):
+    """o/q/k/v: bf16 [batch * n_tok, heads * 64] views; rel_bias f32 [heads, 2 n_tok - 1]; key_valid int32 [batch, n_tok]
+    or None.  softmax(q k^T + bias + mask) v without the 1/sqrt(d) factor (UMT5Attention)."""
+    for t, name in ((o, "o"), (q, "q"), (k, "k"), (v, "v")):
+        _req(t, BF16, "t5_attn " + name)
+        assert t.shape == (batch * n_tok, heads * 64), (name, tuple(t.shape))
+    _req(rel_bias, F32, "t5_attn rel_bias")
+    assert rel_bias.is_contiguous() and rel_bias.shape == (heads, 2 * n_tok - 1)
+    if key_valid is not None:
+        _req(key_valid, torch.int32, "t5_attn key_valid")
+        assert key_valid.is_contiguous() and key_valid.shape == (batch, n_tok)
+    _call("b200tta_t5_attn", _p(o), _ld(o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(rel_bias), _p(key_valid),
+          n_tok, heads, batch, _stream())
