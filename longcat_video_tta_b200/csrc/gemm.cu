@@ -656,6 +656,9 @@ extern "C" int b200tta_gemm(int64_t M, int64_t N, const b200tta_gemm_seg* segs, 
     const bool swiglu = epi->mode == B200TTA_EPI_SWIGLU || epi->mode == B200TTA_EPI_GEGLU;
     B200_REQUIRE(N % 64 == 0, "gemm: N=%lld must be a multiple of 64", (long long)N);
     const int BN = (N % 256 == 0 || N > 256) ? 256 : 64;
+    // (Tried for few-row problems such as the text encoder's 512-token prompts: 128 x 128 single-CTA tiles to fill the chip
+    // -- 128 instead of 32 tiles for a 4096-wide layer.  Slower, 7.6 vs 6.0 ms per UMT5-xxl encode: a 128 x 128 tile pulls
+    // 128 B/clk per SM from L2 where a CTA pair pulls 64, and the L2 cannot feed 128 SMs at that rate.)
     B200_REQUIRE(BN == 64 || N % 32 == 0, "gemm: N tail");
     B200_REQUIRE(!swiglu || (N % 256 == 0), "gemm: SWIGLU / GEGLU need N (=2F) %% 256 == 0");
 

@@ -85,7 +85,7 @@ __device__ __forceinline__ void ta_load_tile(__nv_bfloat16 (*dst)[TA_LD], const 
     }
 }
 
-__global__ void __launch_bounds__(TA_THREADS) t5_attn_kernel(__nv_bfloat16* __restrict__ O, long long ldo,
+__global__ void __launch_bounds__(TA_THREADS, 4) t5_attn_kernel(__nv_bfloat16* __restrict__ O, long long ldo,
                                                              const __nv_bfloat16* __restrict__ Q, long long ldq,
                                                              const __nv_bfloat16* __restrict__ K, long long ldk,
                                                              const __nv_bfloat16* __restrict__ V, long long ldv,
@@ -226,7 +226,7 @@ extern "C" int b200tta_t5_rmsnorm(void* Y, int64_t ldy, const void* X, int64_t l
     B200_REQUIRE(C > 0 && C % 8 == 0 && C <= 4096, "t5_rmsnorm: C=%d must be a multiple of 8, at most 4096", C);
     B200_REQUIRE(aligned16(Y) && aligned16(X) && aligned16(w) && ldy % 8 == 0 && ldx % 8 == 0,
                  "t5_rmsnorm: rows must be 16-byte aligned");
-    const int warps = 8;
+    const int warps = rows >= 148 * 16 ? 8 : 2;     // a 512-token prompt has 512 rows: spread them over every SM
     t5_rmsnorm_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)Y, ldy, (const __nv_bfloat16*)X, ldx, (const __nv_bfloat16*)w, rows, C, eps);
     B200_LAUNCHED();
