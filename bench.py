@@ -695,6 +695,247 @@ def profile_step(ops, fn):
     return out
 
 
+# ------------------------------------------------------------------------------------------------ text-encode workload
+UMT5_XXL = dict(vocab_size=256384, d_model=4096, d_kv=64, d_ff=10240, num_layers=24, num_heads=64,
+                relative_attention_num_buckets=32, relative_attention_max_distance=128, layer_norm_epsilon=1e-6)
+
+
+def _umt5_state(cfg, device, seed=0):
+    """random-init UMT5 encoder weights under transformers' parameter names, bf16, transformers' own initialisation
+    scales (scores of order one, so a bf16 model stays close to fp32 over 24 layers)"""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    d, inner, ff = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"]
+
+    def rn(*shape, std, mean=0.0):
+        return (torch.randn(*shape, generator=g, device=device) * std + mean).to(torch.bfloat16)
+
+    st = {"shared.weight": rn(cfg["vocab_size"], d, std=1.0)}
+    st["encoder.embed_tokens.weight"] = st["shared.weight"]
+    for l in range(cfg["num_layers"]):
+        a, f = f"encoder.block.{l}.layer.0.", f"encoder.block.{l}.layer.1."
+        st[a + "SelfAttention.q.weight"] = rn(inner, d, std=(d * cfg["d_kv"]) ** -0.5)
+        st[a + "SelfAttention.k.weight"] = rn(inner, d, std=d ** -0.5)
+        st[a + "SelfAttention.v.weight"] = rn(inner, d, std=d ** -0.5)
+        st[a + "SelfAttention.o.weight"] = rn(d, inner, std=inner ** -0.5)
+        st[a + "SelfAttention.relative_attention_bias.weight"] = rn(cfg["relative_attention_num_buckets"],
+                                                                    cfg["num_heads"], std=0.5)
+        st[a + "layer_norm.weight"] = rn(d, std=0.1, mean=1.0)
+        st[f + "DenseReluDense.wi_0.weight"] = rn(ff, d, std=d ** -0.5)
+        st[f + "DenseReluDense.wi_1.weight"] = rn(ff, d, std=d ** -0.5)
+        st[f + "DenseReluDense.wo.weight"] = rn(d, ff, std=ff ** -0.5)
+        st[f + "layer_norm.weight"] = rn(d, std=0.1, mean=1.0)
+    st["encoder.final_layer_norm.weight"] = rn(d, std=0.1, mean=1.0)
+    return st
+
+
+def _hf_umt5(cfg, state, dtype, device):
+    """the third-party implementation behind the reference's encode_prompt (common.py:33,62-64,250)"""
+    import torch
+    from transformers import UMT5Config, UMT5EncoderModel
+    c = UMT5Config(vocab_size=cfg["vocab_size"], d_model=cfg["d_model"], d_kv=cfg["d_kv"], d_ff=cfg["d_ff"],
+                   num_layers=cfg["num_layers"], num_heads=cfg["num_heads"],
+                   relative_attention_num_buckets=cfg["relative_attention_num_buckets"],
+                   relative_attention_max_distance=cfg["relative_attention_max_distance"],
+                   layer_norm_epsilon=cfg["layer_norm_epsilon"], feed_forward_proj="gated-gelu", dropout_rate=0.0)
+    with torch.device(device):
+        m = UMT5EncoderModel(c).to(dtype).eval()
+    m.load_state_dict({k: v.to(dtype) for k, v in state.items()}, strict=False)
+    return m
+
+
+def _umt5_work(cfg, B, N):
+    d, inner, ff = cfg["d_model"], cfg["num_heads"] * cfg["d_kv"], cfg["d_ff"]
+    gemm = cfg["num_layers"] * 2 * B * N * (4 * inner * d + 3 * d * ff)
+    attn = cfg["num_layers"] * 4 * B * cfg["num_heads"] * N * N * cfg["d_kv"]
+    return gemm, attn
+
+
+def _text_encode_cpu(budget_layers: int, N: int, n_valid: int, threads: int):
+    """the reference's own implementation (transformers UMT5EncoderModel, fp32) on the host cores: a bounded sample of
+    `budget_layers` of the 24 identical layers at full width, extrapolated by the layer count"""
+    import torch
+    torch.set_num_threads(threads)
+    cfg = dict(UMT5_XXL, num_layers=budget_layers, vocab_size=1024)
+    st = _umt5_state(cfg, "cpu")
+    try:
+        m, kind = _hf_umt5(cfg, st, torch.float32, "cpu"), "reference"
+        fn = lambda ids, mask: m(ids, mask).last_hidden_state     # noqa: E731
+    except Exception:                                             # transformers missing: the oracle port
+        from oracle import umt5_oracle
+        kind = "port"
+        fn = lambda ids, mask: umt5_oracle.umt5_encode(st, cfg, ids, mask)     # noqa: E731
+    ids = torch.randint(2, 1024, (1, N))
+    mask = torch.zeros(1, N, dtype=torch.long)
+    mask[:, :n_valid] = 1
+    with torch.no_grad():
+        fn(ids, mask)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            fn(ids, mask)
+        dt = (time.perf_counter() - t0) / reps
+    scale = UMT5_XXL["num_layers"] / budget_layers
+    return {"value": 1.0 / (dt * scale), "unit": "encodes/s", "cores": threads, "kind": kind + "-extrapolated",
+            "extrapolated": True, "scale_factor": scale, "seconds_timed": dt * reps,
+            "sample": f"transformers UMT5EncoderModel fp32 on {threads} threads: {budget_layers} of 24 identical xxl-width "
+                      f"layers at {N} tokens, {dt:.2f} s per pass, x{scale:.0f} layers = {dt * scale:.1f} s per encode"}
+
+
+def run_text_encode(args):
+    """SURVEY 8(f) row 4, text half: one 512-token prompt through the UMT5-xxl encoder (encode_prompt, common.py:228-255).
+    A "step" is one encode; N > 1 = independent replicas (prompts do not shard), no collective."""
+    import torch
+    import torch.distributed as dist
+    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    N, n_valid = args.text_tokens, 77
+    if args.impl == "reference":
+        if rank == 0:
+            r = _text_encode_cpu(2, N, n_valid, os.cpu_count() or 1)
+            line = {"impl": "reference", "metric": "prompt_encodes_per_sec", "value": r["value"], "unit": "encodes/s",
+                    "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / r["value"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"UMT5-xxl encoder, one {N}-token prompt ({n_valid} real tokens)"},
+                    "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "encodes/s", "h2d_bytes_per_step": 0,
+                                               "d2h_bytes_per_step": 0}, "extrapolated": True}
+            _OUT.write(json.dumps(line) + "\n")
+            _OUT.flush()
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from longcat_video_tta_b200 import ops
+    from longcat_video_tta_b200.text_encoder import B200UMT5Encoder
+    cfg = UMT5_XXL
+    st = _umt5_state(cfg, dev)
+    enc = B200UMT5Encoder(st, device=dev, **{k: v for k, v in cfg.items() if k != "vocab_size"})
+    g = torch.Generator().manual_seed(1 + rank)
+    ids_h = torch.randint(2, cfg["vocab_size"], (1, N), generator=g)
+    mask_h = torch.zeros(1, N, dtype=torch.long)
+    mask_h[:, :n_valid] = 1
+    ids_h[mask_h == 0] = 0
+    ids_h, mask_h = ids_h.pin_memory(), mask_h.pin_memory()
+    ids, mask = ids_h.to(dev), mask_h.to(dev)
+    out_h = torch.empty(1, N, cfg["d_model"], dtype=torch.bfloat16).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    steps = max(args.steps, 20)          # an encode is ~7 ms: time at least 20 of them
+    for _ in range(max(args.warmup, 3)):
+        enc(ids, mask)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    k0 = ops.kernel_launches()
+    ms = timed(lambda: enc(ids, mask), steps)          # 11 GB of weights per encode: far beyond L2
+    launches = ops.kernel_launches() - k0
+    clocks = sampler.stop() if rank == 0 else None
+
+    def e2e():
+        o = enc(ids_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)).last_hidden_state
+        out_h.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+
+    ms_e2e = timed(e2e, steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # per-call device time of one encode (CUDA events on the launching stream around every ABI call)
+    fam, orig = {}, ops._call
+
+    def probe(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *a)
+        e1.record()
+        fam.setdefault(name, []).append((e0, e1))
+
+    ops._call = probe
+    enc(ids, mask)
+    torch.cuda.synchronize()
+    ops._call = orig
+    per = {k: {"calls": len(v), "ms": sum(a.elapsed_time(b) for a, b in v)} for k, v in fam.items()}
+    peaks = measured_peaks()
+    f_gemm, f_attn = _umt5_work(cfg, 1, N)
+    t = ms / steps / 1000.0
+    gm = per["b200tta_gemm"]
+    ach = f_gemm / gm["calls"] / (gm["ms"] / gm["calls"] / 1e3) / 1e12
+    line = {"metric": "prompt_encodes_per_sec", "value": world / t, "unit": "encodes/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"UMT5-xxl encoder (24 layers, d_model 4096, 64 heads x 64, d_ff 10240), one {N}-token "
+                                   f"prompt ({n_valid} real tokens, right-padded) per step, random-init bf16 weights",
+                       "parallelism": f"{world} independent replica(s), no collective",
+                       "l2": "9.3 GB of layer weights streamed per encode: far beyond L2"},
+            "clocks": clocks,
+            "e2e": {"value": world / (ms_e2e / steps / 1000.0), "unit": "encodes/s",
+                    "h2d_bytes_per_step": ids_h.numel() * 8 + mask_h.numel() * 8,
+                    "d2h_bytes_per_step": out_h.numel() * 2},
+            "gpu_launches": launches,
+            "roofline": {"kernel": "gemm2_kernel (q|k|v, o, wi_0|wi_1 + GEGLU, wo; 96 launches per encode)", "bound": "tensor",
+                         "achieved": ach, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": ach / peaks["tflops_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " cuBLAS bf16, sustained figure",
+                         "launches_per_step": gm["calls"], "avg_launch_ms": gm["ms"] / gm["calls"],
+                         "algorithmic_tflop_per_launch": f_gemm / gm["calls"] / 1e12,
+                         "share_of_step": gm["ms"] / sum(v["ms"] for v in per.values()),
+                         "note": "512 rows: a 4096-wide layer is 32 CTA-pair tiles for 74 pairs (DESIGN 6.5)"},
+            "kernel_ms_per_encode": per,
+            "algorithmic_tflop_per_step": (f_gemm + f_attn) / 1e12,
+            "achieved_tflops_per_gpu": (f_gemm + f_attn) / t / 1e12}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = _text_encode_cpu(2, N, n_valid, os.cpu_count() or 1)
+    if world == 1 and args.library_baseline:
+        try:
+            with torch.no_grad():
+                m16 = _hf_umt5(cfg, st, torch.bfloat16, dev)
+                y16 = m16(ids, mask).last_hidden_state.float()
+                ours = enc(ids, mask).last_hidden_state.float()
+                for _ in range(3):
+                    m16(ids, mask)
+                ms_lib = timed(lambda: m16(ids, mask), steps)
+                del m16
+                torch.backends.cuda.matmul.allow_tf32 = False
+                m32 = _hf_umt5(cfg, st, torch.float32, dev)
+                y32 = m32(ids, mask).last_hidden_state
+                del m32
+            rl2 = lambda a, b: float((a - b).norm() / b.norm())     # noqa: E731
+            import transformers
+            line["library_baseline"] = {"impl": f"transformers {transformers.__version__} UMT5EncoderModel, eager bf16, same B200",
+                                        "value": 1000.0 / (ms_lib / steps), "unit": "encodes/s", "ms_per_step": ms_lib / steps,
+                                        "speedup_of_this_repo": ms_lib / ms}
+            line["parity_at_size"] = {"reference": "transformers UMT5EncoderModel fp32 (TF32 off), same bf16-valued weights",
+                                      "ours_rel_l2": rl2(ours, y32), "library_bf16_rel_l2": rl2(y16, y32),
+                                      "ours_cosine": float(torch.dot(ours.flatten(), y32.flatten()) / (ours.norm() * y32.norm()))}
+        except Exception as e:  # noqa: BLE001
+            line["library_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def _protect_stdout():
     """stdout must carry exactly ONE JSON line: route everything else (NCCL banners, library prints) to stderr and
     return a file object bound to the real stdout."""
@@ -727,8 +968,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bsa-sparsity", type=float, default=None,
                     help="block-sparse self-attention (BASELINE.json configs[4], e.g. 0.9375 with --lat-h 96 --lat-w 160)")
+    ap.add_argument("--workload", default="tta_step", choices=["tta_step", "text_encode"],
+                    help="tta_step = BASELINE.json's metric (default); text_encode = SURVEY 8(f) row 4, one prompt per step")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "text_encode":
+        run_text_encode(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.impl == "torch_gpu":
         run_torch_gpu(args)

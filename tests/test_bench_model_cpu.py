@@ -91,3 +91,16 @@ def test_reference_arm_line_says_what_was_timed_and_what_is_extrapolated(monkeyp
     line = json.loads("".join(out))
     assert calls[0] == (1, 1, 2) and calls[1][0] == 4 and calls[1][1] < 20
     assert line["scale_factor"] > 48.0 and "algorithmic-FLOP ratio" in line["cpu_baseline"]["sample"]
+
+
+def test_text_encode_work_model_and_state_names(bench):
+    """bench.py --workload text_encode: algorithmic work of one UMT5-xxl encode and the parameter names its random-init
+    state uses (they must be transformers' names: the oracle's tiny state, pinned to transformers, has the same keys)"""
+    from oracle import umt5_oracle as uo
+    g, a = bench._umt5_work(bench.UMT5_XXL, 1, 512)
+    assert g / 1e12 == pytest.approx(4.742, abs=0.001)      # 24 x 2 x 512 x (4 x 4096^2 + 3 x 4096 x 10240)
+    assert a / 1e9 == pytest.approx(103.1, abs=0.1)         # 24 x 4 x 64 heads x 512^2 x 64
+    assert bench.UMT5_XXL == uo.XXL
+    st = bench._umt5_state(uo.TINY, "cpu")
+    ref = uo.tiny_state(uo.TINY)
+    assert set(st) == set(ref) and all(st[k].shape == ref[k].shape for k in ref)

@@ -171,3 +171,25 @@ def test_encode_prompt_feeds_the_dit_format(ops, golden):
     assert mask.shape == (1, 96) and mask.is_cuda
     ref = c["last_hidden_state_fp32"][:1].cuda()
     assert cos(emb[:, 0], ref) > 0.999
+
+
+def test_from_hf_wraps_a_live_transformers_model(ops, golden):
+    """the drop-in path of INTEGRATION.md: B200UMT5Encoder.from_hf(model) on the object common.py:62-64 loads (bf16, on
+    the GPU), same call, compared with that model in fp32"""
+    tr = pytest.importorskip("transformers")
+    if not hasattr(tr, "UMT5EncoderModel"):
+        pytest.skip("this transformers has no UMT5")
+    from longcat_video_tta_b200.text_encoder import B200UMT5Encoder
+    from oracle.make_golden_umt5 import hf_model
+    cfg = golden["cfg"]
+    st = uo.tiny_state(cfg, seed=11)
+    m32 = hf_model(cfg, st, torch.float32).cuda()
+    m16 = hf_model(cfg, st, torch.bfloat16).cuda()
+    enc = B200UMT5Encoder.from_hf(m16)
+    ids, mask = uo.tiny_inputs(cfg, batch=3, n_tok=72, seed=12)
+    ids, mask = ids.cuda(), mask.cuda()
+    with torch.no_grad():
+        ref, lib = m32(ids, mask).last_hidden_state, m16(ids, mask).last_hidden_state
+    out = enc(ids, mask).last_hidden_state
+    assert out.shape == ref.shape
+    assert rel_l2(out, ref) <= 1.25 * rel_l2(lib, ref) and cos(out, ref) > 0.999
