@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import os
 from dataclasses import dataclass
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn as nn
@@ -257,6 +257,22 @@ class FullGrads:
             self._by_id[id(p)] = self.flat[off: off + p.numel()].view(p.shape)
             off += p.numel()
 
+        # per-block [lo, hi) ranges of the flat buffer (module order keeps a block's parameters contiguous): the unit of
+        # the overlapped gradient all-reduce (stepper.TTAStepper, world > 1)
+        self.block_ranges: List[Tuple[int, int]] = []
+        off = 0
+        spans: Dict[int, List[int]] = {}
+        for n, p in zip(self.names, self.params):
+            if n.startswith("blocks."):
+                b = int(n.split(".")[1])
+                sp = spans.setdefault(b, [off, off])
+                if sp[1] != off:
+                    raise RuntimeError(f"parameters of block {b} are not contiguous in module order")
+                sp[1] = off + p.numel()
+            off += p.numel()
+        for b in sorted(spans):
+            self.block_ranges.append((spans[b][0], spans[b][1]))
+
     def g(self, p) -> torch.Tensor:
         return self._by_id[id(p)]
 
@@ -287,6 +303,9 @@ class TTAEngine:
         self.bsa = dict(sparsity=float(cfgb.get("sparsity", 0.9375)), chunk=tuple(cfgb.get("chunk", (4, 4, 8)))) \
             if getattr(cfg, "enable_bsa", False) else None
         self.full: Optional[FullGrads] = None   # full-model TTA: gradients for every parameter (enable_full_grads)
+        # full-model TTA on several ranks: called with b right after block b's gradients are final, and once (None)
+        # before the late pieces (norm weights, embedders) are written into the flat buffer
+        self.on_block_grads = None
         self._stash = None          # activation stash of the training geometry (see _ensure_stash)
         self._stash_on = False      # the forward in flight writes / the recompute reads the stash
         self.device = dit.x_embedder.proj.weight.device
@@ -1029,7 +1048,11 @@ class TTAEngine:
                     self._block_fwd(b, ws.xs[b], ws.g2, ex, recompute=True)   # block output discarded into g2
             with _Range(f"bwd.block{b}"):
                 self._block_bwd(b, ws.xs[b], ex)
+            if full is not None and self.on_block_grads is not None:
+                self.on_block_grads(b)
         if full is not None:
+            if self.on_block_grads is not None:
+                self.on_block_grads(None)
             self._embedder_grads(ex)
         self._ws_holds = None
         self._stash_on = False

@@ -103,6 +103,14 @@ class TTAStepper:
                 else:
                     e["exp_avg"] = e["exp_avg_sq"] = None
                 entries.append(e)
+            # several ranks: all-reduce each block's 1.1 GB of fp32 gradients as soon as the block's backward is enqueued,
+            # on NCCL's stream, under the remaining blocks' compute (B200TTA_OVERLAP_ALLREDUCE=0: one blocking
+            # all-reduce of the whole 54 GB buffer after the backward)
+            self._pending = []
+            if self.world > 1 and os.environ.get("B200TTA_OVERLAP_ALLREDUCE", "1") != "0":
+                self.eng.on_block_grads = self._reduce_block_grads
+            else:
+                self.eng.on_block_grads = None
         self._n_lora_entries = len(entries)
         self._extra_entries = []
         for p in self.extra_params:
@@ -205,9 +213,41 @@ class TTAStepper:
             return False
         return (ex.need_dmod or ex.norm_grads or any(h is not None for h in ex.hidden) or ex.hidden_final is not None)
 
+    def _reduce_block_grads(self, b: Optional[int]):
+        import torch.distributed as dist
+        if b is None:      # the late pieces are about to be written into ranges that are being reduced: order them behind
+            for w in self._pending:
+                w.wait()   # stream-level wait, the host does not block
+            self._pending = [True]     # marks "block ranges are done" for _sync_grads
+            return
+        lo, hi = self.eng.full.block_ranges[b]
+        self._pending.append(dist.all_reduce(self.eng.full.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _sync_full_grads_overlapped(self):
+        """what the per-block all-reduces have not covered: the ranges before / after the blocks (embedders, final layer)
+        and the norm weights inside the block ranges, which the engine writes after the block loop"""
+        import torch.distributed as dist
+        fg = self.eng.full
+        flat, ranges = fg.flat, fg.block_ranges
+        for lo, hi in ((0, ranges[0][0]), (ranges[-1][1], flat.numel())):
+            if hi > lo:
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+        named = fg.named()
+        late = [named[k] for k in self.extras.d_norm if k.startswith("blocks.")]
+        if late:
+            buf = torch.cat([t.reshape(-1) for t in late])
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.pg)
+            off = 0
+            for t in late:
+                t.copy_(buf[off: off + t.numel()].view(t.shape))
+                off += t.numel()
+        self._pending = []
+
     def _sync_grads(self):
         if self.world > 1:
             from .dist import all_reduce_grads
+            if self.full and self._pending:
+                return self._sync_full_grads_overlapped()
             if self.full:
                 bufs = [self.eng.full.flat]
             else:
