@@ -133,3 +133,56 @@ def test_scripts_under_torchrun_host_flow(tmp_path):
     ck = json.loads((tmp_path / "checkpoint.json").read_text())
     assert ck["next_idx"] == 2 and len(ck["results"]) == 2
     assert (tmp_path / "summary.json").exists() and (tmp_path / "config.json").exists()
+
+
+def _overlap_worker(rank, world, port, out):
+    """host logic of the overlapped full-model gradient all-reduce (stepper._reduce_block_grads /
+    _sync_full_grads_overlapped) on gloo, with a stand-in for the engine's flat buffer"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from types import SimpleNamespace
+
+    from longcat_video_tta_b200 import dist as D
+    from longcat_video_tta_b200.stepper import TTAStepper
+    D.init_from_env("gloo")
+    # layout: [embedders 7 | block 0: w 10, norm 3 | block 1: w 10, norm 3 | final 5]
+    names = ["emb.w", "blocks.0.w", "blocks.0.norm.weight", "blocks.1.w", "blocks.1.norm.weight", "final.w"]
+    sizes = [7, 10, 3, 10, 3, 5]
+    flat = torch.zeros(sum(sizes))
+    views, off = {}, 0
+    for n, k in zip(names, sizes):
+        views[n] = flat[off: off + k]
+        off += k
+    gen = torch.Generator().manual_seed(100 + rank)
+    local = torch.randn(flat.numel(), generator=gen)
+    lv, off = {}, 0
+    for n, k in zip(names, sizes):
+        lv[n] = local[off: off + k]
+        off += k
+    full = SimpleNamespace(flat=flat, block_ranges=[(7, 20), (20, 33)], named=lambda: views)
+    extras = SimpleNamespace(d_norm={"blocks.1.norm.weight": None, "blocks.0.norm.weight": None})
+    st = SimpleNamespace(eng=SimpleNamespace(full=full), pg=None, _pending=[], extras=extras)
+    # the engine's order: final layer first, blocks from the last to the first (norm weights NOT yet written), then the
+    # "late" call, then norm weights and embedders, then the optimizer's sync
+    views["final.w"].copy_(lv["final.w"])
+    for b in (1, 0):
+        views[f"blocks.{b}.w"].copy_(lv[f"blocks.{b}.w"])
+        TTAStepper._reduce_block_grads(st, b)
+    assert len(st._pending) == 2
+    TTAStepper._reduce_block_grads(st, None)
+    for b in (1, 0):
+        views[f"blocks.{b}.norm.weight"].copy_(lv[f"blocks.{b}.norm.weight"])
+    views["emb.w"].copy_(lv["emb.w"])
+    TTAStepper._sync_full_grads_overlapped(st)
+    assert st._pending == []
+    out[rank] = dict(local=local, reduced=flat.clone())
+    dist.destroy_process_group()
+
+
+def test_overlapped_full_gradient_allreduce_covers_every_element_once():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, port, out), nprocs=world, join=True)
+    want = out[0]["local"] + out[1]["local"]
+    for r in range(world):
+        assert torch.equal(out[r]["reduced"], want)      # each element summed over the ranks exactly once
