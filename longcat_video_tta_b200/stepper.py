@@ -106,7 +106,7 @@ class TTAStepper:
             # several ranks: all-reduce each block's 1.1 GB of fp32 gradients as soon as the block's backward is enqueued,
             # on NCCL's stream, under the remaining blocks' compute (B200TTA_OVERLAP_ALLREDUCE=0: one blocking
             # all-reduce of the whole 54 GB buffer after the backward)
-            self._pending = []
+            self._pending, self._blocks_reduced = [], False
             if self.world > 1 and os.environ.get("B200TTA_OVERLAP_ALLREDUCE", "1") != "0":
                 self.eng.on_block_grads = self._reduce_block_grads
             else:
@@ -218,8 +218,10 @@ class TTAStepper:
         if b is None:      # the late pieces are about to be written into ranges that are being reduced: order them behind
             for w in self._pending:
                 w.wait()   # stream-level wait, the host does not block
-            self._pending = [True]     # marks "block ranges are done" for _sync_grads
+            self._pending = []
+            self._blocks_reduced = True
             return
+        self._blocks_reduced = False       # (a backward whose gradients were never applied leaves nothing behind)
         lo, hi = self.eng.full.block_ranges[b]
         self._pending.append(dist.all_reduce(self.eng.full.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
 
@@ -241,12 +243,12 @@ class TTAStepper:
             for t in late:
                 t.copy_(buf[off: off + t.numel()].view(t.shape))
                 off += t.numel()
-        self._pending = []
+        self._blocks_reduced = False
 
     def _sync_grads(self):
         if self.world > 1:
             from .dist import all_reduce_grads
-            if self.full and self._pending:
+            if self.full and getattr(self, "_blocks_reduced", False):
                 return self._sync_full_grads_overlapped()
             if self.full:
                 bufs = [self.eng.full.flat]

@@ -160,7 +160,7 @@ def _overlap_worker(rank, world, port, out):
         off += k
     full = SimpleNamespace(flat=flat, block_ranges=[(7, 20), (20, 33)], named=lambda: views)
     extras = SimpleNamespace(d_norm={"blocks.1.norm.weight": None, "blocks.0.norm.weight": None})
-    st = SimpleNamespace(eng=SimpleNamespace(full=full), pg=None, _pending=[], extras=extras)
+    st = SimpleNamespace(eng=SimpleNamespace(full=full), pg=None, _pending=[], _blocks_reduced=False, extras=extras)
     # the engine's order: final layer first, blocks from the last to the first (norm weights NOT yet written), then the
     # "late" call, then norm weights and embedders, then the optimizer's sync
     views["final.w"].copy_(lv["final.w"])
@@ -172,8 +172,9 @@ def _overlap_worker(rank, world, port, out):
     for b in (1, 0):
         views[f"blocks.{b}.norm.weight"].copy_(lv[f"blocks.{b}.norm.weight"])
     views["emb.w"].copy_(lv["emb.w"])
+    assert st._pending == [] and st._blocks_reduced
     TTAStepper._sync_full_grads_overlapped(st)
-    assert st._pending == []
+    assert not st._blocks_reduced
     out[rank] = dict(local=local, reduced=flat.clone())
     dist.destroy_process_group()
 
