@@ -379,6 +379,19 @@ __device__ __forceinline__ void sts_b32(uint32_t saddr, uint32_t v) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// barrier over `nthreads` threads that also ORs a predicate across them (every participant gets the result)
+__device__ __forceinline__ bool named_bar_red_or(int id, int nthreads, bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.u32 q, %3, 0;\n\t"
+        "bar.red.or.pred p, %1, %2, q;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(r)
+        : "r"(id), "r"(nthreads), "r"((uint32_t)pred)
+        : "memory");
+    return r != 0;
+}
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
