@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
             mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
         }
         for (int t = 0; t < TILES; ++t) {
-            mbar_init(&s_full[t], 1); mbar_init(&p_full[t], BM); mbar_init(&o_done[t], 1); mbar_init(&p_half[t], BM);
+            mbar_init(&s_full[t], 1); mbar_init(&p_full[t], BM / 32); mbar_init(&o_done[t], 1); mbar_init(&p_half[t], BM / 32);
         }
         fence_barrier_init();
     }
@@ -336,9 +336,11 @@ __global__ void __launch_bounds__(fwd_threads(TILES), 1) attn_fwd_kernel(const _
             l += lsum;
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&p_half[t]);    // no early hand-over of the first half here: P is final only after the check
+            // one arrival per warp: 256 per-thread arrivals per tile and block are 256 shared-memory operations in the
+            // queue the MUFU instructions go through, and each one wakes every warp sleeping on a barrier of this CTA
+            mbar_arrive_warp(&p_half[t]);    // no early hand-over of the first half here: P is final only after the check
             TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 3);
-            mbar_arrive(&p_full[t]);
+            if (lane == 0) mbar_arrive(&p_full[t]);
             TL_MARK(quarter == 0 && lane == 0, j, 5 * t + 4);
         }
         // ---- epilogue: O_t / l -> bf16 ; LSE
