@@ -323,6 +323,15 @@ int b200tta_gather_rows(void* dst, int64_t ldd, const void* src, int64_t lds, co
 /* out[c] = sum over rows of A[row, c]  (bf16 in, f32 out; bias gradients of full-model TTA). */
 int b200tta_colsum(float* out, const void* A, int64_t lda, int64_t rows, int32_t C, b200tta_stream_t stream);
 
+/* VAE latent normalisation, the reference-owned part of SURVEY 8f row 4's VAE half: normalize_latents / denormalize_latents
+ * (delta_experiment/scripts/common.py:175-205) on a dense [B, channels, T, H, W] latent (inner = T * H * W, n = total
+ * elements).  inverse = 0: out = (x - mean[c]) * inv_std[c]; inverse = 1: out = x / inv_std[c] + mean[c]; bf16 (is_bf16)
+ * or f32 in and out, every intermediate rounded to that dtype as torch does.  mean / inv_std f32 [channels], already
+ * rounded to the latent dtype by the caller.  The VAE network itself (upstream AutoencoderKLWan) is not part of this
+ * library. */
+int b200tta_latent_affine(void* out, const void* in, const float* mean, const float* inv_std, int64_t n, int64_t inner,
+                          int32_t channels, int32_t is_bf16, int32_t inverse, b200tta_stream_t stream);
+
 /* ---- text encoder (text half): encode_prompt, delta_experiment/scripts/common.py:228-255, which calls
  * transformers' UMT5EncoderModel.  Linear layers go through b200tta_gemm (B200TTA_EPI_GEGLU for wi_0 | wi_1,
  * B200TTA_EPI_GATE_RESID with gate NULL for the residual adds), the embedding lookup through b200tta_gather_rows. */

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200tta_colsum": [vp, vp, i64, i64, i32, vp],
     "b200tta_gather_rows": [vp, i64, vp, i64, vp, i64, i32, vp],
     "b200tta_t5_rmsnorm": [vp, i64, vp, i64, vp, i64, i32, f32, vp],
+    "b200tta_latent_affine": [vp, vp, vp, vp, i64, i64, i32, i32, i32, vp],
     "b200tta_t5_attn": [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, i32, i32, i32, vp],
 }
 

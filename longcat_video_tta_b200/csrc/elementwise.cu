@@ -693,6 +693,31 @@ inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
     return (int)(g > cap ? cap : g);
 }
 
+// ------------------------------------------------------------------------------------ VAE latent normalisation
+// normalize_latents / denormalize_latents of the reference (delta_experiment/scripts/common.py:175-205) on a
+// [B, C, T, H, W] latent: out = (x - mean[c]) * inv_std[c]   or   out = x / inv_std[c] + mean[c], with the reference's
+// rounding points (every intermediate is rounded to the latent dtype: two roundings per element for bf16).
+template <bool BF16IO, bool INVERSE>
+__global__ void __launch_bounds__(256) latent_affine_kernel(void* __restrict__ out_, const void* __restrict__ in_,
+                                                            const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                                            long long n, long long inner, int channels) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c = (int)((i / inner) % channels);
+        const float m = __ldg(mean + c), s = __ldg(inv_std + c);
+        if (BF16IO) {
+            const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(in_);
+            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_);
+            const float x = __bfloat162float(in[i]);
+            const float t = __bfloat162float(__float2bfloat16_rn(INVERSE ? __fdiv_rn(x, s) : x - m));
+            out[i] = __float2bfloat16_rn(INVERSE ? t + m : t * s);
+        } else {
+            const float x = reinterpret_cast<const float*>(in_)[i];
+            reinterpret_cast<float*>(out_)[i] = INVERSE ? __fadd_rn(__fdiv_rn(x, s), m) : __fmul_rn(__fsub_rn(x, m), s);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace b200
 
@@ -978,6 +1003,25 @@ extern "C" int b200tta_latent_to_tokens(void* tokens, const float* latent, int32
     B200_REQUIRE(tokens && latent && T > 0 && t_begin >= 0 && t_begin < T && H % 2 == 0 && W % 2 == 0, "latent_to_tokens: bad arguments");
     const long long total = (long long)(T - t_begin) * (H / 2) * (W / 2) * 64;
     latent_to_tokens_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)tokens, latent, T, H, W, t_begin);
+    B200_LAUNCHED();
+    return B200TTA_OK;
+}
+
+extern "C" int b200tta_latent_affine(void* out, const void* in, const float* mean, const float* inv_std, int64_t n,
+                                     int64_t inner, int32_t channels, int32_t is_bf16, int32_t inverse,
+                                     b200tta_stream_t stream) {
+    if (int rc = require_sm100()) return rc;
+    B200_REQUIRE(out && in && mean && inv_std && n > 0 && inner > 0 && channels > 0 && n % (inner * channels) == 0,
+                 "latent_affine: n=%lld must be batch x channels=%d x inner=%lld", (long long)n, channels, (long long)inner);
+    const int grid = grid_for(n, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16) {
+        if (inverse) latent_affine_kernel<true, true><<<grid, 256, 0, st>>>(out, in, mean, inv_std, n, inner, channels);
+        else latent_affine_kernel<true, false><<<grid, 256, 0, st>>>(out, in, mean, inv_std, n, inner, channels);
+    } else {
+        if (inverse) latent_affine_kernel<false, true><<<grid, 256, 0, st>>>(out, in, mean, inv_std, n, inner, channels);
+        else latent_affine_kernel<false, false><<<grid, 256, 0, st>>>(out, in, mean, inv_std, n, inner, channels);
+    }
     B200_LAUNCHED();
     return B200TTA_OK;
 }

@@ -366,3 +366,18 @@ def t5_attn(o, q, k, v, rel_bias, key_valid, n_tok: int, heads: int, batch: int)
         assert key_valid.is_contiguous() and key_valid.shape == (batch, n_tok)
     _call("b200tta_t5_attn", _p(o), _ld(o), _p(q), _ld(q), _p(k), _ld(k), _p(v), _ld(v), _p(rel_bias), _p(key_valid),
           n_tok, heads, batch, _stream())
+
+
+# ------------------------------------------------------------------------------------------------ VAE latents
+def latent_affine(out, x, mean, inv_std, inverse: bool):
+    """out = (x - mean[c]) * inv_std[c]  (inverse: x / inv_std[c] + mean[c]) on a dense [B, C, T, H, W] latent, bf16 or f32"""
+    if x.dtype not in (BF16, F32) or out.dtype != x.dtype:
+        raise TypeError(f"latent_affine: bf16 or f32 latents, got {x.dtype} -> {out.dtype}")
+    _req(x, x.dtype, "latent_affine x")
+    _req(mean, F32, "latent_affine mean")
+    _req(inv_std, F32, "latent_affine inv_std")
+    assert x.dim() == 5 and x.is_contiguous() and out.is_contiguous() and out.shape == x.shape
+    Cn = x.shape[1]
+    assert mean.numel() == Cn and inv_std.numel() == Cn
+    _call("b200tta_latent_affine", _p(out), _p(x), _p(mean), _p(inv_std), x.numel(), x[0, 0].numel(), Cn,
+          int(x.dtype == BF16), int(bool(inverse)), _stream())
