@@ -1,5 +1,7 @@
 """Command-line entry points with the reference's flags and output layout:
 
+  lora_experiment/scripts/run_full_tta.py        --learning-rate --num-steps --warmup-steps --weight-decay --max-grad-norm
+                                                 --optimizer {sgd,adamw}          (every DiT parameter trains)
   lora_experiment/scripts/run_lora_tta.py        --lora-rank --lora-alpha --target-ffn --target-modules
                                                  --lora-target-blocks --use-builtin-lora --save-lora-weights
                                                  --learning-rate --num-steps --warmup-steps --weight-decay --max-grad-norm
@@ -26,13 +28,14 @@ import torch
 
 from . import adapters as A
 from . import dist as D
+from . import full as F
 from . import lora as L
 from .common import resolve_tta_frames, split_tta_latents, validate_tta_feature_budget
 from .dit import B200DiT
 from .early_stopping import add_early_stopping_args, build_early_stopper_from_args
 
 BF16 = torch.bfloat16
-METHODS = ("lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film")
+METHODS = ("lora", "full", "delta_a", "delta_b", "delta_c", "norm_tune", "film")
 
 
 # ---- the reference's command-line surface, one row per flag: (flag, kind, default[, choices]) with kind in
@@ -72,6 +75,9 @@ _METHOD_FLAGS = {
              ("--use-builtin-lora", "on", False), ("--save-lora-weights", "on", False), ("--learning-rate", float, 2e-4),
              ("--num-steps", int, 20), ("--warmup-steps", int, 3), ("--weight-decay", float, 0.01),
              ("--max-grad-norm", float, 1.0)],                                   # run_lora_tta.py:671-698
+    "full": [("--learning-rate", float, 1e-5), ("--num-steps", int, 10), ("--warmup-steps", int, 2),
+             ("--weight-decay", float, 0.01), ("--max-grad-norm", float, 1.0),
+             ("--optimizer", str, "sgd", ["sgd", "adamw"])],                    # run_full_tta.py:341-351
     "delta_a": [("--delta-steps", int, 20), ("--delta-lr", float, 1e-3)],       # run_delta_a.py:376-377
     "delta_b": [("--delta-steps", int, 20), ("--delta-lr", float, 1e-3), ("--num-groups", int, 4),
                 ("--delta-target", str, "timestep", ["timestep", "hidden"]), ("--delta-dim", int, None),
@@ -157,7 +163,7 @@ def experiment_config(method: str, args, adapter_cfg: Dict, frames: Dict) -> Dic
     ``model`` and the recorded-only groups of ``outside_the_step``."""
     flat = _clip_gate_flat(args)
     impl = adapter_cfg.get("lora", {}).get("implementation")
-    cfg = {"method": f"lora_tta_{impl}" if method == "lora" else method, **adapter_cfg,
+    cfg = {"method": f"lora_tta_{impl}" if method == "lora" else ("full_tta" if method == "full" else method), **adapter_cfg,
            "generation": {"num_cond_frames": args.num_cond_frames, "num_frames": args.num_frames,
                           "gen_start_frame": args.gen_start_frame, "num_inference_steps": args.num_inference_steps,
                           "guidance_scale": args.guidance_scale, "resolution": args.resolution},
@@ -173,6 +179,7 @@ def experiment_config(method: str, args, adapter_cfg: Dict, frames: Dict) -> Dic
 # run_film_tta.py:676-)
 _SUMMARY_HEAD = {
     "lora": ("lora_tta", ("lora_rank", "lora_alpha", "learning_rate", "num_steps")),
+    "full": ("full_tta", ("learning_rate", "num_steps")),                       # run_full_tta.py:865-868
     "delta_a": ("delta_a", ("delta_steps", "delta_lr")),
     "delta_b": ("delta_b", ("delta_target", "delta_target_blocks", "num_groups", "delta_steps", "delta_lr")),
     "delta_c": ("delta_c", ("delta_mode", "delta_steps", "delta_lr")),
@@ -190,7 +197,8 @@ def summary_record(method: str, args, results: List[Dict]) -> Dict:
     losses = [r["final_loss"] for r in ok if r.get("final_loss") is not None]
     name, head = _SUMMARY_HEAD[method]
     gated = [r for r in ok if r.get("clip_gate_enabled")]
-    return {"method": name, **{k: getattr(args, k) for k in head},
+    extra = {"total_params": getattr(args, "_total_params", None)} if method == "full" else {}     # run_full_tta.py:874
+    return {"method": name, **{k: getattr(args, k) for k in head}, **extra,
             "num_cond_frames": args.num_cond_frames, "num_frames": args.num_frames, "gen_start_frame": args.gen_start_frame,
             "batch_videos": args.batch_videos, "retrieval_pool_dir": args.retrieval_pool_dir,
             "num_videos": len(results), "num_successful": len(ok), "num_failed": len(results) - len(ok),
@@ -275,11 +283,11 @@ def run(method: str, argv=None) -> Dict:
             "common.load_longcat_components / encode_video / encode_prompt, load the DiT weights into B200DiT "
             "(INTEGRATION.md 1a) and call longcat_video_tta_b200.lora.finetune_lora_on_conditioning")
 
-    if args.batch_videos > 1 and method not in ("lora", "delta_a"):
-        raise NotImplementedError("--batch-videos > 1 exists for LoRA (finetune_lora_batch) and delta-A "
-                                  "(_optimize_delta_a_batch) only, as in the reference")
+    if args.batch_videos > 1 and method not in ("lora", "full", "delta_a"):
+        raise NotImplementedError("--batch-videos > 1 exists for LoRA (finetune_lora_batch), full-model TTA "
+                                  "(finetune_full_batch) and delta-A (_optimize_delta_a_batch) only, as in the reference")
 
-    total, ctx, n_lat, n_ctx_lat = frame_budget(args, context="lora_tta" if method == "lora" else method)
+    total, ctx, n_lat, n_ctx_lat = frame_budget(args, context={"lora": "lora_tta", "full": "full_tta"}.get(method, method))
     dit = B200DiT.random_init(args.model, seed=0, device=device)
     cfg = dit.config
     hw = tuple(int(x) for x in args.latent_hw.split(",")) if args.latent_hw else (60, 104)
@@ -303,6 +311,17 @@ def run(method: str, argv=None) -> Dict:
                        "training": {"learning_rate": args.learning_rate, "num_steps": args.num_steps,
                                     "warmup_steps": args.warmup_steps, "weight_decay": args.weight_decay,
                                     "max_grad_norm": args.max_grad_norm}}
+    elif method == "full":
+        # run_full_tta.py:449-462: every DiT parameter trains; the base state is kept on the host and restored per video
+        for p in dit.parameters():
+            p.requires_grad = True
+        total_params = sum(p.numel() for p in dit.parameters())
+        args._total_params = total_params
+        base_state = {k: v.detach().cpu().clone() for k, v in dit.state_dict().items()}
+        adapter_cfg = {"training": {"learning_rate": args.learning_rate, "num_steps": args.num_steps,
+                                    "warmup_steps": args.warmup_steps, "weight_decay": args.weight_decay,
+                                    "max_grad_norm": args.max_grad_norm, "optimizer": args.optimizer,
+                                    "total_params": total_params, "trainable_params": total_params}}
     elif method == "delta_a":
         wrapper = A.DeltaAWrapper(dit, cfg.adaln_tembed_dim)
     elif method == "delta_b":
@@ -322,7 +341,7 @@ def run(method: str, argv=None) -> Dict:
     elif method == "film":
         wrapper = A.FiLMAdapterWrapper(dit, num_groups=args.num_groups, hidden_size=cfg.hidden_size, film_mode=args.film_mode)
         wrapper.apply_to_dit()
-    if method != "lora":
+    if method not in ("lora", "full"):
         n_train = sum(p.numel() for p in wrapper.trainable())
         adapter_cfg = {method: {k: v for k, v in vars(args).items() if k.startswith(("delta", "norm", "film", "num_groups", "also_tune"))},
                        "trainable_params": n_train}
@@ -343,13 +362,15 @@ def run(method: str, argv=None) -> Dict:
                   "batch_size": 1, "num_neighbors": 0}
         try:
             cond, train, val = split_tta_latents(vid["latents"], n_ctx_lat, args.es_holdout_fraction)
-            model = dit if method == "lora" else wrapper
+            model = dit if method in ("lora", "full") else wrapper
             if world > 1:       # replicas re-initialise identically ...
                 torch.manual_seed(args.seed + 1_000_003 * (idx + 1))
             # reset the adapter for every video (run_lora_tta.py:1127)
             if method == "lora":
                 (L.reset_builtin_lora_weights if args.use_builtin_lora else L.reset_lora_weights)(mods)
                 dit.engine.resolve_sites()
+            elif method == "full":
+                F.reset_dit_weights(dit, base_state)            # run_full_tta.py: per-video reset from the host copy
             elif method == "norm_tune":
                 A.restore_params(norm_params, init_norm)
             else:
@@ -360,9 +381,13 @@ def run(method: str, argv=None) -> Dict:
             batch_mode = args.batch_videos > 1      # the reference's batch loops run without the early stopper
             es = early_stopper if (early_stopper is not None and val is not None and not batch_mode) else None
             if es is not None:
-                save_fn = (lambda: [p.data.clone() for p in (L.get_lora_parameters(mods) if method == "lora" else wrapper.trainable())])
-                es.setup(model, cond, val, vid["prompt_embeds"], vid["prompt_mask"], device=device, dtype=BF16,
-                         video_id=vid["video_name"], save_fn=save_fn)
+                if method == "full":    # run_full_tta.py:722-741: no save_fn, the stopper's default snapshot covers the model
+                    es.setup(model, cond, val, vid["prompt_embeds"], vid["prompt_mask"], device=device, dtype=BF16,
+                             video_id=vid["video_name"])
+                else:
+                    save_fn = (lambda: [p.data.clone() for p in (L.get_lora_parameters(mods) if method == "lora" else wrapper.trainable())])
+                    es.setup(model, cond, val, vid["prompt_embeds"], vid["prompt_mask"], device=device, dtype=BF16,
+                             video_id=vid["video_name"], save_fn=save_fn)
             if batch_mode:
                 # retrieval-augmented batch (run_lora_tta.py:1037-1062, run_delta_a.py:~640 build it from the pool; here:
                 # the evaluation video + K-1 further synthetic videos), held on the host and visited round-robin
@@ -377,10 +402,21 @@ def run(method: str, argv=None) -> Dict:
                 r = L.finetune_lora_batch(dit, mods, batch, num_steps=args.num_steps, lr=args.learning_rate,
                                           warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
                                           max_grad_norm=args.max_grad_norm, device=device, dtype=BF16)
+            elif batch_mode and method == "full":
+                r = F.finetune_full_batch(dit, batch, num_steps=args.num_steps, lr=args.learning_rate,
+                                          warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
+                                          max_grad_norm=args.max_grad_norm, device=device, dtype=BF16,
+                                          optimizer_type=args.optimizer)
             elif batch_mode:
                 t0 = time.time()
                 r = A._optimize_delta_a_batch(wrapper, batch, num_steps=args.delta_steps, lr=args.delta_lr, device=device)
                 r["train_time"] = time.time() - t0
+            elif method == "full":
+                r = F.finetune_full_on_conditioning(dit, cond, train, vid["prompt_embeds"], vid["prompt_mask"],
+                                                    num_steps=args.num_steps, lr=args.learning_rate,
+                                                    warmup_steps=args.warmup_steps, weight_decay=args.weight_decay,
+                                                    max_grad_norm=args.max_grad_norm, device=device, dtype=BF16,
+                                                    early_stopper=es, optimizer_type=args.optimizer)
             elif method == "lora":
                 variants = None
                 if args.aug_enabled and args.aug_flip:

@@ -205,9 +205,7 @@ def run_rows(commands: Sequence[Tuple[str, str, List[str]]], gpus: int = 1, pyth
                 done[nxt] = {"run_id": run_id, "returncode": None}
             else:
                 if not (root / script).is_file():
-                    raise NotImplementedError(
-                        f"{script} is not part of this build (for full-model TTA only the functions exist: "
-                        "longcat_video_tta_b200.full.finetune_full_on_conditioning / finetune_full_batch)")
+                    raise NotImplementedError(f"{script} is not part of this build")
                 env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(gpu)) if gpus > 1 else None
                 log = open(log_dir / f"{run_id}.log", "w") if log_dir else None
                 print(f"  Starting {run_id} on GPU {gpu}: {shlex.join(cmd)}")

@@ -81,8 +81,6 @@ def dict_keys(src: str, opener: str):
 def main():
     table = {}
     for method, (name, folder) in SCRIPTS.items():
-        if method == "full":
-            continue
         src = (folder / f"{name}.py").read_text()
         summary, cut = dict_keys(src, "    summary = {")
         config, _ = dict_keys(src, "    exp_config = {")

@@ -89,7 +89,7 @@ def test_parse_target_blocks_matches_reference_golden(golden_dir):
             assert got == want, (key, spec, n, got, want)
 
 
-@pytest.mark.parametrize("method", ["lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
+@pytest.mark.parametrize("method", ["lora", "full", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
 def test_flag_surface_matches_reference_golden(golden_dir, method):
     """Every flag the reference's own parser declares (oracle/make_golden_cli_flags.py executes the parser section of
     each script's main()) exists here with the same dest, type, default, choices, nargs, const and action class.  The one
@@ -180,6 +180,61 @@ def test_run_lora_batch_and_flip_variant_host_flow(tmp_path, monkeypatch, golden
     assert calls[-1][3] is None and s["results"][0]["batch_size"] == 1
 
 
+def test_run_full_host_flow(tmp_path, monkeypatch, golden_dir):
+    """lora_experiment/scripts/run_full_tta.py through cli.run with the GPU pieces stubbed: every parameter is made trainable,
+    the base state is restored before every video (run_full_tta.py:455-462), single and batch loops get the reference's
+    arguments, the files carry the reference's keys"""
+    import json
+    import types
+    import torch
+    lin = torch.nn.Linear(4, 3)
+    for p in lin.parameters():
+        p.requires_grad = False
+    dit = types.SimpleNamespace(config=types.SimpleNamespace(caption_channels=32, adaln_tembed_dim=512, hidden_size=64, out_channels=16),
+                                parameters=lin.parameters, state_dict=lin.state_dict)
+    monkeypatch.setattr(cli.B200DiT, "random_init", staticmethod(lambda *a, **k: dit))
+    calls, resets = [], []
+
+    def reset(d, base):
+        resets.append({k: v.clone() for k, v in base.items()})
+
+    def single(d, cond, train, pe, pm, **kw):
+        assert all(p.requires_grad for p in lin.parameters())
+        with torch.no_grad():
+            lin.weight.add_(1.0)          # "training" changes the model; the next video must start from the base state
+        calls.append(("single", cond.shape[2], train.shape[2], kw))
+        return {"losses": [2.0, 1.0], "train_time": 0.2, "es_check_time": 0.0, "early_stopping_info": None}
+
+    def batch(d, batch_data, **kw):
+        calls.append(("batch", batch_data, kw))
+        return {"losses": [1.0] * kw["num_steps"], "train_time": 0.2, "es_check_time": 0.0, "early_stopping_info": None}
+
+    monkeypatch.setattr(cli.F, "reset_dit_weights", reset)
+    monkeypatch.setattr(cli.F, "finetune_full_on_conditioning", single)
+    monkeypatch.setattr(cli.F, "finetune_full_batch", batch)
+    base_w = lin.weight.detach().clone()
+    base = ("--synthetic --model tiny --device cpu --latent-hw 8,8 --tta-total-frames 17 --tta-context-frames 5 "
+            "--max-videos 2 --es-disable --num-steps 3 --optimizer adamw --learning-rate 2e-5")
+    s = cli.run("full", f"--output-dir {tmp_path / 'f'} {base}".split())
+    assert [c[0] for c in calls] == ["single", "single"] and calls[0][1:3] == (2, 2)
+    kw = calls[0][3]
+    assert (kw["num_steps"], kw["lr"], kw["warmup_steps"], kw["optimizer_type"], kw["early_stopper"]) == (3, 2e-5, 2, "adamw", None)
+    assert len(resets) == 2 and all(torch.equal(r["weight"], base_w) for r in resets)      # the host copy of the BASE state
+    assert s["method"] == "full_tta" and s["total_params"] == 15 and s["num_successful"] == 2
+    layout = json.loads((golden_dir / "output_layout.json").read_text())["full"]
+    cfg = json.loads((tmp_path / "f" / "config.json").read_text())
+    _covers(cfg, layout["config"])
+    assert cfg["method"] == "full_tta" and cfg["training"]["trainable_params"] == 15 and cfg["training"]["optimizer"] == "adamw"
+    written = json.loads((tmp_path / "f" / "summary.json").read_text())
+    assert [k for k in layout["summary_keys"] if k not in written] == []
+    rec = written["results"][0]
+    want = set(layout["result_keys"]) | (set(layout["result_keys_later"]) - {"gen_time", "output_path"})
+    assert want <= set(rec), want - set(rec)
+    s = cli.run("full", f"--output-dir {tmp_path / 'fb'} {base} --batch-videos 3".split())
+    kind, data, kw = calls[-1]
+    assert kind == "batch" and len(data) == 3 and kw["optimizer_type"] == "adamw" and s["results"][0]["batch_size"] == 3
+
+
 @pytest.mark.parametrize("method,flags", [("delta_b", "--batch-videos 4"), ("film", "--batch-videos 2")])
 def test_unbuilt_combinations_fail_loudly(tmp_path, method, flags):
     with pytest.raises(NotImplementedError):
@@ -193,7 +248,7 @@ def _covers(have, want, path=""):
             _covers(have[k], sub, f"{path}{k}.")
 
 
-@pytest.mark.parametrize("method", ["lora", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
+@pytest.mark.parametrize("method", ["lora", "full", "delta_a", "delta_b", "delta_c", "norm_tune", "film"])
 def test_output_files_carry_the_reference_keys(golden_dir, method):
     """config.json / summary.json hold every key of the reference's own dict literals (oracle/make_golden_output_layout.py
     reads them out of each main(); four scripts are cut short in the snapshot, their keys up to the cut are checked) and
@@ -214,16 +269,21 @@ def test_output_files_carry_the_reference_keys(golden_dir, method):
     empty = cli.summary_record(method, args, [])
     assert empty["avg_train_time"] == 0 and empty["avg_final_loss"] == 0 and empty["num_successful"] == 0
     json.dumps(s)
-    if layout["config"]:
+    if layout["config"] and method == "lora":
         adapter = {"lora": {k: 0 for k in layout["config"]["lora"]}, "training": {k: 0 for k in layout["config"]["training"]}}
         adapter["lora"]["implementation"] = "builtin"
         cfg = cli.experiment_config(method, args, adapter, {"total": 2})
         _covers(cfg, layout["config"])
         assert cfg["method"] == "lora_tta_builtin" and cfg["clip_gate"]["sampling_mode"] == "late_only"
+    if method == "full":
+        assert "total_params" in s
+        cfg = cli.experiment_config(method, args, {"training": {k: 0 for k in layout["config"]["training"]}}, {"total": 2})
+        _covers(cfg, layout["config"])
+        assert cfg["method"] == "full_tta" and cfg["clip_gate"]["sampling_mode"] == "late_only"
 
 
 @pytest.mark.parametrize("method,loop_out", [
-    ("lora", {}), ("delta_a", {"delta_norm": 0.1}), ("delta_b", {"delta_norms": [0.1, 0.2]}),
+    ("lora", {}), ("full", {}), ("delta_a", {"delta_norm": 0.1}), ("delta_b", {"delta_norms": [0.1, 0.2]}),
     ("delta_c", {"delta_out_norm": 0.1, "delta_out_values": [0.0] * 16}), ("norm_tune", {}), ("film", {"correction_norm": 0.3}),
 ])
 def test_per_video_record_carries_the_reference_keys(golden_dir, method, loop_out):

@@ -110,4 +110,4 @@ def test_rows_run_as_local_processes_one_per_gpu(tmp_path):
     gpus = [(tmp_path / f"R{i}.log").read_text().split()[0] for i in range(5)]
     assert set(gpus) == {"0", "1"} and gpus[0] != gpus[1]
     with pytest.raises(NotImplementedError):
-        sweep.run_rows([("F1", "lora_experiment/scripts/run_full_tta.py", [])])
+        sweep.run_rows([("F1", "baseline_experiment/scripts/run_open_sora.py", [])])     # a reference method outside this build
