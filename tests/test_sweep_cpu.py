@@ -49,8 +49,6 @@ def test_every_reference_command_line_parses_here(golden):
     reference's parser would put them (spot-checked on the method's own hyper-parameters)."""
     n = 0
     for r in golden["rows"]:
-        if r["method"] == "full":
-            continue                                   # full-model TTA is out of scope: no script to parse it
         args = cli.build_parser(r["method"]).parse_args(r["argv"][1:])
         merged = {**r["fixed"], **{k: v for k, v in r["row"].items() if k != "run_id"}}
         for key, val in merged.items():
@@ -60,7 +58,7 @@ def test_every_reference_command_line_parses_here(golden):
             assert got == (type(got)(val) if got is not None else val), (r["config"], r["run_id"], key, got, val)
         assert args.no_save_videos and args.clip_gate_fail_open
         n += 1
-    assert n == 204
+    assert n == len(golden["rows"]) == 260
 
 
 def test_unknown_key_unset_bool_and_overrides():
